@@ -1,0 +1,33 @@
+"""
+feinsum_b200 -- B200-native execution backend for feinsum's batched einsums.
+
+Front-end (``array`` / ``einsum`` / ``batched_einsum`` / ``BatchedEinsum``)
+is API-compatible with kaushikcfd/feinsum 2025.3 (reference
+``src/feinsum/__init__.py:37-68``); kernels are hand-written sm_100a CUDA
+reached through a C ABI (``include/fnsm_b200.h``).  There is no CPU fallback.
+"""
+
+from feinsum_b200.cl_utils import CudaDevice, CudaQueue, FakeCLDevice
+from feinsum_b200.contraction_schedule import (
+    get_opt_einsum_contraction_schedule,
+    get_trivial_contraction_schedule,
+)
+from feinsum_b200.diagnostics import (
+    CudaBackendError,
+    InvalidParameterError,
+    NoDevicePeaksInfoError,
+    NoFactInDatabaseError,
+    TransformValidationError,
+)
+from feinsum_b200.einsum import (
+    Array,
+    BatchedEinsum,
+    EinsumAxisAccess,
+    FreeAxis,
+    SizeParam,
+    SummationAxis,
+)
+from feinsum_b200.make_einsum import array, batched_einsum, einsum
+from feinsum_b200.utils import IndexNameGenerator
+
+__version__ = "2025.3+b200.r1"

@@ -1,0 +1,450 @@
+"""
+CUDA "code generation": BatchedEinsum -> kernel plan -> executor.
+
+Takes the place of the reference's ``feinsum.codegen.loopy.generate_loopy``
+(reference ``src/feinsum/codegen/loopy.py:112-325``).  Where the reference
+builds a loopy ``TranslationUnit`` that transform scripts then rewrite, this
+module *classifies* the einsum into one of the hand-written sm_100a kernel
+families and returns a :class:`CudaProgram` -- the object a "transform"
+(``TransformT``: ``(program, insn_match=None, kernel_name=None) -> program``)
+decorates with launch parameters and that yields an executor with the loopy
+calling convention (reference ``measure.py:163-165,244-251``)::
+
+    program  = generate_cuda(einsum)                 # ~ generate_loopy(einsum)
+    program  = transform(program, insn_match=None, kernel_name=None)
+    executor = program.executor(cq)                  # ~ t_unit.executor(cq, **args)
+    evt, outs = executor(cq, **arrays)               # outs: {"_fe_out": tensor, ...}
+    evt.wait()
+
+Arrays are ``torch`` CUDA tensors used purely as device-buffer carriers; all
+arithmetic happens in ``libfnsm_b200.so`` behind ``include/fnsm_b200.h``.
+
+Kernel families:
+
+=================  ============================  ===============================
+kernel_id          subscripts (up to renaming)   C ABI
+=================  ============================  ===============================
+``grad``           ``xre,rij,ej->xei``           ``fnsm_b200_opmat_batch``
+``div``            ``xre,rij,xej->ei``           ``fnsm_b200_opmat_batch``
+``lift_ef``        ``ef,fij,fej->ei``            ``fnsm_b200_opmat_batch``
+``lift_fe``        ``ifj,fe,fej->ei``            ``fnsm_b200_opmat_batch``
+``tensor_product`` ``eabc,ia->eibc`` (+2 modes)  ``fnsm_b200_tensor_product``
+``generic``        anything else                 ``fnsm_b200_generic_einsum``
+=================  ============================  ===============================
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field, replace
+from itertools import permutations
+from typing import Any
+
+import numpy as np
+
+from feinsum_b200 import _cabi
+from feinsum_b200._immutable import Map
+from feinsum_b200.cl_utils import CudaQueue, as_queue
+from feinsum_b200.contraction_schedule import ContractionSchedule
+from feinsum_b200.einsum import INT_CLASSES, BatchedEinsum, SizeParam
+from feinsum_b200.make_einsum import parse_subscripts
+
+_DTYPE_CODE = {np.dtype("float64"): _cabi.FNSM_F64, np.dtype("float32"): _cabi.FNSM_F32}
+
+
+# {{{ structural matching (renaming- and operand-order-invariant)
+
+
+def match_subscripts(
+    einsum: BatchedEinsum, pattern: str
+) -> tuple[tuple[int, ...], dict[str, str]] | None:
+    """
+    Match *einsum* against *pattern* (e.g. ``"xre,rij,ej->xei"``) up to index
+    renaming and operand order; axis order inside every operand and in the
+    output must agree (it fixes the memory layout the kernels assume).
+
+    Returns ``(perm, index_map)``: pattern operand ``k`` is einsum operand
+    ``perm[k]``; ``index_map`` maps pattern letters to the einsum's.
+    """
+    p_out, p_ins = parse_subscripts(pattern)
+    if len(p_ins) != einsum.n or len(p_out) != len(einsum.out_idx_set):
+        return None
+    for perm in permutations(range(einsum.n)):
+        fwd: dict[str, str] = {}
+        bwd: dict[str, str] = {}
+        ok = True
+        pairs = [(p_out, einsum.out_idx_set)]
+        pairs += [(p_ins[k], einsum.in_idx_sets[perm[k]]) for k in range(einsum.n)]
+        for p_idx, e_idx in pairs:
+            if len(p_idx) != len(e_idx):
+                ok = False
+                break
+            for a, b in zip(p_idx, e_idx):
+                if fwd.setdefault(a, b) != b or bwd.setdefault(b, a) != a:
+                    ok = False
+                    break
+            if not ok:
+                break
+        if ok:
+            return tuple(perm), fwd
+    return None
+
+
+# }}}
+
+
+@dataclass(frozen=True)
+class KernelPlan:
+    """Which kernel family executes the einsum, and how its operands map."""
+
+    kernel_id: str
+    #: pattern operand k is einsum operand perm[k]
+    perm: tuple[int, ...] = ()
+    #: small integer facts the launch needs (n_outer, n_i, n_j, n1d, mode, ...)
+    facts: Map[str, int] = field(default_factory=Map)
+    #: name of the symbolic (long) index, "" if the einsum has none
+    long_index: str = ""
+
+
+_OPMAT_PATTERNS = (
+    ("grad", "xre,rij,ej->xei", _cabi.OP_GRAD),
+    ("div", "xre,rij,xej->ei", _cabi.OP_DIV),
+    ("lift_ef", "ef,fij,fej->ei", _cabi.OP_LIFT_EF),
+    ("lift_fe", "ifj,fe,fej->ei", _cabi.OP_LIFT_FE),
+)
+_TP_PATTERNS = ("eabc,ia->eibc", "eabc,ib->eaic", "eabc,ic->eabi")
+
+
+def _uniform_dtype(einsum: BatchedEinsum) -> np.dtype[Any] | None:
+    dts = set(einsum.arg_to_dtype.values())
+    if len(dts) == 1:
+        (dt,) = dts
+        if np.dtype(dt) in _DTYPE_CODE:
+            return np.dtype(dt)
+    return None
+
+
+def _is_long(einsum: BatchedEinsum, idx: str) -> bool:
+    return isinstance(einsum.index_to_dim_length[idx], SizeParam)
+
+
+def _int_extent(einsum: BatchedEinsum, idx: str) -> int | None:
+    ext = einsum.index_to_dim_length[idx]
+    return int(ext) if isinstance(ext, INT_CLASSES) else None
+
+
+def classify(einsum: BatchedEinsum) -> KernelPlan:
+    """Pick the kernel family for *einsum* (never fails: ``generic`` is total
+    over what the generic kernel supports; unsupported dtypes raise at
+    executor construction)."""
+    dt = _uniform_dtype(einsum)
+    if dt is not None:
+        for kid, pattern, _ in _OPMAT_PATTERNS:
+            m = match_subscripts(einsum, pattern)
+            if m is None:
+                continue
+            perm, imap = m
+            e = imap["e"]
+            others = [imap[k] for k in imap if k != "e"]
+            if not _is_long(einsum, e) or any(_is_long(einsum, o) for o in others):
+                continue
+            names = parse_subscripts(pattern)[1]
+            # operand roles in the pattern: which operand carries the fields?
+            field_pos = 2
+            shared_ok = all(
+                len({row[perm[k]].name for row in einsum.args}) == 1
+                for k in range(3)
+                if k != field_pos
+            )
+            if not shared_ok:
+                continue
+            if kid in ("grad", "div"):
+                nx, nr = _int_extent(einsum, imap["x"]), _int_extent(einsum, imap["r"])
+                if nx != nr:
+                    continue
+                n_outer = nx
+            else:
+                n_outer = _int_extent(einsum, imap["f"])
+            del names
+            return KernelPlan(
+                kid,
+                perm,
+                Map(
+                    n_outer=int(n_outer),  # type: ignore[arg-type]
+                    n_i=int(_int_extent(einsum, imap["i"])),  # type: ignore[arg-type]
+                    n_j=int(_int_extent(einsum, imap["j"])),  # type: ignore[arg-type]
+                ),
+                e,
+            )
+        if einsum.n == 2:
+            for mode, pattern in enumerate(_TP_PATTERNS):
+                m = match_subscripts(einsum, pattern)
+                if m is None:
+                    continue
+                perm, imap = m
+                if not _is_long(einsum, imap["e"]):
+                    continue
+                exts = {_int_extent(einsum, imap[k]) for k in "abci"}
+                if len(exts) != 1 or None in exts:
+                    continue
+                (n1d,) = exts
+                if not 2 <= int(n1d) <= 8:  # type: ignore[arg-type]
+                    continue
+                return KernelPlan(
+                    "tensor_product", perm, Map(n1d=int(n1d), mode=mode), imap["e"]  # type: ignore[arg-type]
+                )
+    longs = [i for i in einsum.index_to_dim_length if _is_long(einsum, i)]
+    return KernelPlan("generic", tuple(range(einsum.n)), Map(), longs[0] if longs else "")
+
+
+class LaunchEvent:
+    """What an executor call returns in place of a ``pyopencl.Event``."""
+
+    def __init__(self, torch_event: Any):
+        self._evt = torch_event
+
+    def wait(self) -> None:
+        self._evt.synchronize()
+
+    @property
+    def torch_event(self) -> Any:
+        return self._evt
+
+
+@dataclass(frozen=True)
+class CudaProgram:
+    """
+    The unit a transform acts on (stand-in for ``loopy.TranslationUnit``).
+
+    ``params`` are the launch-configuration fields of ``fnsm_cfg``
+    (``variant``, ``tile_e``, ``threads``, ``stages``, ``ctas_per_sm``);
+    transforms return ``program.with_params(...)``.
+    """
+
+    einsum: BatchedEinsum
+    plan: KernelPlan
+    schedule: ContractionSchedule | None = None
+    params: Map[str, int] = field(default_factory=Map)
+
+    @property
+    def kernel_id(self) -> str:
+        return self.plan.kernel_id
+
+    def with_params(self, **params: int) -> "CudaProgram":
+        return replace(self, params=self.params.update(params))
+
+    def executor(self, cq: Any = None, **_unused_args: Any) -> "CudaExecutor":
+        return CudaExecutor(self, as_queue(cq))
+
+
+def generate_cuda(
+    einsum: BatchedEinsum, schedule: ContractionSchedule | None = None
+) -> CudaProgram:
+    """Lower *einsum* to a :class:`CudaProgram` (cf. ``generate_loopy``).
+
+    *schedule* is recorded for API parity; the specialised kernels implement
+    the flop-optimal order (the reference's hoisting transforms do the same),
+    the generic kernel the trivial one -- results agree within round-off
+    (reference ``test/test_codegen.py:123-165`` checks exactly that).
+    """
+    if not isinstance(einsum, BatchedEinsum):
+        raise TypeError("generate_cuda expects a BatchedEinsum")
+    return CudaProgram(einsum, classify(einsum), schedule)
+
+
+def _torch() -> Any:
+    import torch
+
+    return torch
+
+
+def _np_dtype_of(t: Any) -> np.dtype[Any]:
+    torch = _torch()
+    return np.dtype(
+        {torch.float64: "float64", torch.float32: "float32"}.get(t.dtype, "object")
+    )
+
+
+class CudaExecutor:
+    """Callable with the loopy-executor convention (see module docstring)."""
+
+    def __init__(self, program: CudaProgram, cq: CudaQueue):
+        self.program = program
+        self.einsum = program.einsum
+        self.plan = program.plan
+        self.cq = cq
+        self.lib = _cabi.lib()  # raises CudaBackendError when the .so is missing
+        self.output_names = list(self.einsum.output_names)
+        self._cfg = _cabi.make_cfg(dict(program.params))
+        row_dtypes = [
+            np.result_type(*[a.dtype for a in row]) for row in self.einsum.args
+        ]
+        self.out_dtypes = [np.dtype(d) for d in row_dtypes]
+        if self.plan.kernel_id == "generic":
+            for row, rd in zip(self.einsum.args, self.out_dtypes):
+                if rd not in _DTYPE_CODE or any(np.dtype(a.dtype) != rd for a in row):
+                    raise NotImplementedError(
+                        "generic CUDA einsum supports uniform float32/float64 "
+                        f"operands per row, got {[str(a.dtype) for a in row]}"
+                    )
+
+    # -- shape handling --------------------------------------------------
+    def _bind_sizes(self, arrays: dict[str, Any]) -> dict[str, int]:
+        """Infer every symbolic extent from the arrays passed in."""
+        sizes: dict[str, int] = {}
+        for name, shape in self.einsum.arg_to_shape.items():
+            if name not in arrays:
+                raise TypeError(f"missing input array '{name}'")
+            arr = arrays[name]
+            if tuple(arr.shape).__len__() != len(shape):
+                raise ValueError(
+                    f"'{name}': expected rank {len(shape)}, got shape {tuple(arr.shape)}"
+                )
+            for dim, got in zip(shape, arr.shape):
+                if isinstance(dim, SizeParam):
+                    if sizes.setdefault(dim.name, int(got)) != int(got):
+                        raise ValueError(
+                            f"inconsistent values for size parameter '{dim.name}'"
+                        )
+                elif int(dim) != int(got):
+                    raise ValueError(
+                        f"'{name}': expected shape {shape}, got {tuple(arr.shape)}"
+                    )
+        return sizes
+
+    def _concrete(self, shape: tuple[Any, ...], sizes: dict[str, int]) -> tuple[int, ...]:
+        return tuple(
+            sizes[d.name] if isinstance(d, SizeParam) else int(d) for d in shape
+        )
+
+    def _check_input(self, name: str, arr: Any) -> None:
+        torch = _torch()
+        if not isinstance(arr, torch.Tensor):
+            raise TypeError(
+                f"'{name}': expected a torch CUDA tensor (device buffer carrier), "
+                f"got {type(arr).__name__}"
+            )
+        if not arr.is_cuda or arr.device.index != self.cq.device.index:
+            raise ValueError(f"'{name}' must live on {self.cq.torch_device}")
+        if not arr.is_contiguous():
+            raise ValueError(f"'{name}' must be C-contiguous")
+        if _np_dtype_of(arr) != np.dtype(self.einsum.arg_to_dtype[name]):
+            raise TypeError(
+                f"'{name}': dtype {arr.dtype} != {self.einsum.arg_to_dtype[name]}"
+            )
+
+    # -- call ------------------------------------------------------------
+    def __call__(
+        self, cq: Any = None, allocator: Any = None, **arrays: Any
+    ) -> tuple[LaunchEvent, dict[str, Any]]:
+        torch = _torch()
+        q = self.cq if cq is None else as_queue(cq)
+        ins = {k: v for k, v in arrays.items() if k in self.einsum.all_args}
+        for name, arr in ins.items():
+            self._check_input(name, arr)
+        sizes = self._bind_sizes(ins)
+        out_shape = self._concrete(self.einsum.shape, sizes)
+        outs: dict[str, Any] = {}
+        for oname, odt in zip(self.output_names, self.out_dtypes):
+            tdt = torch.float64 if odt == np.dtype("float64") else torch.float32
+            if oname in arrays and arrays[oname] is not None:
+                o = arrays[oname]
+                if tuple(o.shape) != out_shape or o.dtype != tdt or not o.is_contiguous():
+                    raise ValueError(f"output '{oname}' has wrong shape/dtype/layout")
+                outs[oname] = o
+            else:
+                outs[oname] = torch.empty(out_shape, dtype=tdt, device=q.torch_device)
+        unknown = set(arrays) - set(self.einsum.all_args) - set(self.output_names)
+        if unknown:
+            raise TypeError(f"unexpected arguments: {sorted(unknown)}")
+
+        with torch.cuda.device(q.torch_device):
+            with torch.cuda.stream(q.torch_stream):
+                if all(o.numel() > 0 for o in outs.values()):
+                    self._launch(q, ins, outs, sizes)
+                evt = torch.cuda.Event()
+                evt.record(q.torch_stream)
+        return LaunchEvent(evt), outs
+
+    # -- per-family launches ----------------------------------------------
+    def _launch(
+        self, q: CudaQueue, ins: dict[str, Any], outs: dict[str, Any], sizes: dict[str, int]
+    ) -> None:
+        kid = self.plan.kernel_id
+        stream = C.c_void_p(q.stream)
+        es = self.einsum
+        if kid in ("grad", "div", "lift_ef", "lift_fe"):
+            kind = {k: c for k, _, c in _OPMAT_PATTERNS}[kid]
+            perm = self.plan.perm
+            # pattern operand order: grad/div/lift_ef = (jac, op, field); lift_fe = (op, jac, field)
+            jac_pos, op_pos = (1, 0) if kid == "lift_fe" else (0, 1)
+            row0 = es.args[0]
+            jac = ins[row0[perm[jac_pos]].name]
+            op = ins[row0[perm[op_pos]].name]
+            b = es.b
+            fields = (C.c_void_p * b)(*[ins[row[perm[2]].name].data_ptr() for row in es.args])
+            out_ptrs = (C.c_void_p * b)(*[outs[n].data_ptr() for n in self.output_names])
+            E = sizes[es.index_to_dim_length[self.plan.long_index].name]  # type: ignore[union-attr]
+            f = self.plan.facts
+            rc = self.lib.fnsm_b200_opmat_batch(
+                kind, _DTYPE_CODE[self.out_dtypes[0]],
+                C.c_void_p(jac.data_ptr()), C.c_void_p(op.data_ptr()),
+                fields, out_ptrs, b, f["n_outer"], f["n_i"], f["n_j"],
+                C.c_int64(E), self._cfg, stream,
+            )
+            _cabi.check(rc, f"fnsm_b200_opmat_batch[{kid}]")
+        elif kid == "tensor_product":
+            perm = self.plan.perm
+            E = sizes[es.index_to_dim_length[self.plan.long_index].name]  # type: ignore[union-attr]
+            f = self.plan.facts
+            for row, oname in zip(es.args, self.output_names):
+                A = ins[row[perm[0]].name]
+                M = ins[row[perm[1]].name]
+                rc = self.lib.fnsm_b200_tensor_product(
+                    _DTYPE_CODE[self.out_dtypes[0]],
+                    C.c_void_p(A.data_ptr()), C.c_void_p(M.data_ptr()),
+                    C.c_void_p(outs[oname].data_ptr()),
+                    f["n1d"], f["mode"], C.c_int64(E), self._cfg, stream,
+                )
+                _cabi.check(rc, "fnsm_b200_tensor_product")
+        else:
+            self._launch_generic(ins, outs, sizes, stream)
+
+    def _launch_generic(
+        self, ins: dict[str, Any], outs: dict[str, Any], sizes: dict[str, int], stream: Any
+    ) -> None:
+        es = self.einsum
+        free = list(es.out_idx_set)
+        summed = list(es.sum_indices)
+        order = free + summed
+        if len(order) > _cabi.MAX_INDICES or es.n > _cabi.MAX_OPERANDS:
+            raise NotImplementedError("einsum too large for the generic CUDA kernel")
+        extent = {
+            idx: (sizes[d.name] if isinstance(d, SizeParam) else int(d))
+            for idx, d in es.index_to_dim_length.items()
+        }
+        desc = _cabi.EinsumDesc()
+        desc.n_free, desc.n_sum, desc.n_operands = len(free), len(summed), es.n
+        desc.dtype = _DTYPE_CODE[self.out_dtypes[0]]
+        for k, idx in enumerate(order):
+            desc.extent[k] = extent[idx]
+        # output strides (C order over out_idx_set)
+        stride = 1
+        for k in range(len(free) - 1, -1, -1):
+            desc.out_stride[k] = stride
+            stride *= extent[free[k]]
+        for iop, idx_set in enumerate(es.in_idx_sets):
+            st = 1
+            strides: dict[str, int] = {}
+            for idx in reversed(idx_set):
+                strides[idx] = strides.get(idx, 0) + st
+                st *= extent[idx]
+            for k, idx in enumerate(order):
+                desc.in_stride[iop][k] = strides.get(idx, 0)
+        b = es.b
+        in_ptrs = (C.c_void_p * (b * es.n))(
+            *[ins[a.name].data_ptr() for row in es.args for a in row]
+        )
+        out_ptrs = (C.c_void_p * b)(*[outs[n].data_ptr() for n in self.output_names])
+        rc = self.lib.fnsm_b200_generic_einsum(C.byref(desc), b, in_ptrs, out_ptrs, stream)
+        _cabi.check(rc, "fnsm_b200_generic_einsum")

@@ -1,0 +1,144 @@
+// C-ABI entry points of the operator-matrix x element-batch einsum classes
+// (DG gradient / divergence / face-mass lift) and of the fused wave_3d_p4
+// operator; dispatch between kernel variants.
+//
+// replaces: reference generate_loopy + tuning/impls/{xre_rij_ej_to_xei,
+// xre_rij_xej_to_ei*, ifj_fe_fej_to_ei*, batched_*}.py + the executor launch
+// in src/feinsum/measure.py:244-273.
+#include "common.cuh"
+#include "opmat_simt.cuh"
+#include "opmat_dmma.cuh"
+#include <cstdio>
+#include <cstring>
+
+namespace fnsm {
+
+static void set_range(fnsm_cfg_range* r, const char* name, int lo, int hi, int step, int dflt) {
+  std::memset(r, 0, sizeof(*r));
+  std::snprintf(r->name, sizeof(r->name), "%s", name);
+  r->lo = lo; r->hi = hi; r->step = step; r->dflt = dflt;
+}
+
+int opmat_cfg_space(int kernel_id, fnsm_cfg_range* out, int cap) {
+  (void)kernel_id;
+  fnsm_cfg_range tmp[5];
+  int n = 0;
+  set_range(&tmp[n++], "variant", 0, 1, 1, 1);        // 0 = simt, 1 = dmma (fp64, tuned shapes)
+  set_range(&tmp[n++], "tile_e", 8, 64, 8, 16);        // simt: elements per CTA tile
+  set_range(&tmp[n++], "ctas_per_sm", 1, 8, 1, 0);     // persistent grid size
+  set_range(&tmp[n++], "threads", 64, 512, 32, 0);     // dmma: 32*(consumer warps)+32
+  set_range(&tmp[n++], "stages", 2, 16, 1, 0);         // dmma: ring slots beyond one per warp
+  for (int i = 0; i < n && i < cap; ++i) out[i] = tmp[i];
+  return n;
+}
+
+template <typename T>
+static int launch_simt(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows,
+                       int n_outer, int ni, int nj, long long E, const fnsm_cfg* cfg,
+                       const DevInfo& di, cudaStream_t st) {
+  int tile_e = (cfg && cfg->tile_e > 0) ? cfg->tile_e : 16;
+  if (tile_e < 1 || tile_e > 256) return FNSM_E_BAD_CONFIG;
+  if (n_outer > 4 && (kind == FNSM_OP_GRAD || kind == FNSM_OP_DIV)) return FNSM_E_UNSUPPORTED;
+  size_t smem = 0;
+  if (kind == FNSM_OP_GRAD)
+    smem = sizeof(T) * ((size_t)n_outer * ni * nj + (size_t)tile_e * nj + (size_t)n_outer * n_outer * tile_e);
+  else if (kind == FNSM_OP_DIV)
+    smem = sizeof(T) * ((size_t)n_outer * ni * nj + (size_t)n_outer * tile_e * nj + (size_t)n_outer * n_outer * tile_e);
+  else
+    smem = sizeof(T) * ((size_t)n_outer * ni * nj + (size_t)n_outer * tile_e * nj + (size_t)n_outer * tile_e);
+  if (smem > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
+  const long long ntiles = (E + tile_e - 1) / tile_e;
+  int cps = (cfg && cfg->ctas_per_sm > 0) ? cfg->ctas_per_sm : 4;
+  long long grid = (long long)cps * di.sms;
+  if (grid > ntiles) grid = ntiles;
+  const T* J = static_cast<const T*>(jac);
+  const T* O = static_cast<const T*>(op);
+  cudaError_t e = cudaSuccess;
+#define FNSM_LAUNCH(KERNEL)                                                                  \
+  do {                                                                                       \
+    e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return (int)e;                                                     \
+    KERNEL<<<(unsigned)grid, 256, smem, st>>>(J, O, rows, nrows, n_outer, ni, nj, E, tile_e); \
+  } while (0)
+  switch (kind) {
+    case FNSM_OP_GRAD: FNSM_LAUNCH(k_grad_simt<T>); break;
+    case FNSM_OP_DIV: FNSM_LAUNCH(k_div_simt<T>); break;
+    case FNSM_OP_LIFT_EF: FNSM_LAUNCH((k_lift_simt<T, false>)); break;
+    case FNSM_OP_LIFT_FE: FNSM_LAUNCH((k_lift_simt<T, true>)); break;
+    default: return FNSM_E_BAD_ARG;
+  }
+#undef FNSM_LAUNCH
+  return post_launch();
+}
+
+static int opmat_dispatch(int kind, int dtype, const void* jac, const void* op,
+                          const void* const* fields, void* const* outs, int b,
+                          int n_outer, int ni, int nj, long long E, const fnsm_cfg* cfg,
+                          cudaStream_t st) {
+  DevInfo di;
+  if (int rc = device_info(&di)) return rc;
+  int variant = cfg ? cfg->variant : -1;   // -1: library default
+  if (variant < -1 || variant > 1) return FNSM_E_BAD_CONFIG;
+  const bool dmma_ok = dtype == FNSM_F64 && dmma_supported(kind, n_outer, ni, nj);
+  if (variant == 1 && !dmma_ok) return FNSM_E_UNSUPPORTED;
+  if (variant == -1) variant = dmma_ok ? 1 : 0;
+  for (int r0 = 0; r0 < b; r0 += 8) {
+    const int nr = (b - r0 < 8) ? (b - r0) : 8;
+    OpmatRows rows{};
+    for (int r = 0; r < nr; ++r) {
+      rows.field[r] = fields[r0 + r];
+      rows.out[r] = outs[r0 + r];
+      if (!rows.field[r] || !rows.out[r]) return FNSM_E_BAD_ARG;
+    }
+    int rc;
+    if (variant == 1)
+      rc = launch_dmma(kind, jac, op, rows, nr, n_outer, ni, nj, E, cfg, di, st);
+    else if (dtype == FNSM_F64)
+      rc = launch_simt<double>(kind, jac, op, rows, nr, n_outer, ni, nj, E, cfg, di, st);
+    else
+      rc = launch_simt<float>(kind, jac, op, rows, nr, n_outer, ni, nj, E, cfg, di, st);
+    if (rc) return rc;
+  }
+  return FNSM_OK;
+}
+
+}  // namespace fnsm
+
+extern "C" int fnsm_b200_opmat_batch(int32_t kind, int32_t dtype, const void* jac, const void* op,
+                                     const void* const* fields, void* const* outs, int32_t b,
+                                     int32_t n_outer, int32_t n_i, int32_t n_j, int64_t E,
+                                     const fnsm_cfg* cfg, void* stream) {
+  using namespace fnsm;
+  if (!jac || !op || !fields || !outs || b <= 0 || E < 0) return FNSM_E_BAD_ARG;
+  if (kind < FNSM_OP_GRAD || kind > FNSM_OP_LIFT_FE) return FNSM_E_BAD_ARG;
+  if (dtype != FNSM_F64 && dtype != FNSM_F32) return FNSM_E_UNSUPPORTED;
+  if (n_outer < 1 || n_i < 1 || n_j < 1) return FNSM_E_BAD_ARG;
+  if (E == 0) return FNSM_OK;
+  return opmat_dispatch(kind, dtype, jac, op, fields, outs, b, n_outer, n_i, n_j, E, cfg,
+                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fnsm_b200_wave3d_fused(int32_t dtype, const fnsm_wave_args* a, int64_t E,
+                                      const fnsm_cfg* cfg, void* stream) {
+  using namespace fnsm;
+  if (!a || E < 0) return FNSM_E_BAD_ARG;
+  if (dtype != FNSM_F64 && dtype != FNSM_F32) return FNSM_E_UNSUPPORTED;
+  if (!a->J || !a->D || !a->v || !a->u || !a->L || !a->Jface || !a->div_out || !a->grad_out)
+    return FNSM_E_BAD_ARG;
+  for (int k = 0; k < 4; ++k)
+    if (!a->F[k] || !a->lift_out[k]) return FNSM_E_BAD_ARG;
+  if (E == 0) return FNSM_OK;
+  DevInfo di;
+  if (int rc = device_info(&di)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == FNSM_F64 && (!cfg || cfg->variant != 0))
+    return launch_wave3d_dmma(a, E, cfg, di, st);
+  // variant 0 / fp32: three back-to-back launches of the simt kernels on one stream
+  const void* f1[1] = {a->v}; void* o1[1] = {a->div_out};
+  int rc = opmat_dispatch(FNSM_OP_DIV, dtype, a->J, a->D, f1, o1, 1, 3, 35, 35, E, cfg, st);
+  if (rc) return rc;
+  const void* f2[1] = {a->u}; void* o2[1] = {a->grad_out};
+  rc = opmat_dispatch(FNSM_OP_GRAD, dtype, a->J, a->D, f2, o2, 1, 3, 35, 35, E, cfg, st);
+  if (rc) return rc;
+  return opmat_dispatch(FNSM_OP_LIFT_FE, dtype, a->Jface, a->L, a->F, a->lift_out, 4, 4, 35, 15, E, cfg, st);
+}

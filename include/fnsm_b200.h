@@ -1,0 +1,198 @@
+/*
+ * fnsm_b200.h -- C ABI of the B200-native batched-einsum backend.
+ *
+ * This is the drop-in boundary for feinsum's execution path.  The reference
+ * (kaushikcfd/feinsum 2025.3) has no native interface: a kernel is launched
+ * from Python as
+ *
+ *     executor = t_unit.executor(cq, **arg_dict)        (src/feinsum/measure.py:163, 244)
+ *     evt, outs = executor(cq, allocator=..., **arg_dict)   (measure.py:164, 251, 268)
+ *
+ * where t_unit comes from generate_loopy() + a transform script
+ * (src/feinsum/codegen/loopy.py:112-325, src/feinsum/tuning/impls/...).  The
+ * functions below are what a feinsum executor binds instead (ctypes/cffi);
+ * each entry cites the reference code path it replaces.
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer owned by the caller, C-contiguous,
+ *     laid out exactly as the einsum's operand shapes with the symbolic axis
+ *     bound to E (reference measure.py:91-97, 226-233).  No allocation and no
+ *     synchronisation happens inside; launches are asynchronous on `stream`
+ *     (a cudaStream_t passed as void*), like the reference's in-order queue.
+ *   - return value: 0 on success, a positive cudaError_t, or a negative
+ *     FNSM_E_* code.  fnsm_b200_strerror() decodes all three.
+ *   - thread safety: entry points keep no mutable global state except a
+ *     per-device attribute cache guarded by a mutex; concurrent calls on
+ *     distinct streams are safe.
+ *   - `cfg` may be NULL (built-in default launch configuration).  A config
+ *     outside the legal space yields FNSM_E_BAD_CONFIG -- the tuner maps that
+ *     to InvalidParameterError (reference tuning/__init__.py:557-559).
+ */
+#ifndef FNSM_B200_H
+#define FNSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FNSM_ABI_VERSION 1
+
+/* dtype codes (reference: BatchedEinsum.arg_to_dtype, einsum.py:262-272) */
+enum { FNSM_F64 = 0, FNSM_F32 = 1 };
+
+/* error codes */
+enum {
+  FNSM_OK = 0,
+  FNSM_E_BAD_ARG = -1,       /* null pointer, negative size, unknown enum  */
+  FNSM_E_UNSUPPORTED = -2,   /* shape/dtype has no compiled instantiation  */
+  FNSM_E_BAD_CONFIG = -3,    /* launch configuration outside legal space   */
+  FNSM_E_ALIGNMENT = -4,     /* pointer not aligned for the requested path */
+  FNSM_E_NO_DEVICE = -5
+};
+
+/* "operator matrix x element batch" einsum classes */
+enum {
+  FNSM_OP_GRAD = 0,    /* xre,rij,ej->xei   J(X,R,E) D(R,I,J) u(E,J)        -> out(X,E,I)  */
+  FNSM_OP_DIV = 1,     /* xre,rij,xej->ei   J(X,R,E) D(R,I,J) u(X,E,J)      -> out(E,I)    */
+  FNSM_OP_LIFT_EF = 2, /* ef,fij,fej->ei    J(E,F)   R(F,I,J) v_k(F,E,J)    -> out_k(E,I)  */
+  FNSM_OP_LIFT_FE = 3  /* ifj,fe,fej->ei    L(I,F,J) J(F,E)   v_k(F,E,J)    -> out_k(E,I)  */
+};
+
+/*
+ * Launch configuration: the CUDA replacement of a loopy transform script's
+ * parameters (reference tuning/impls/xre_rij_ej_to_xei.py:14-38: n_e_per_wg,
+ * nwork_items_per_e, i_tiles, j_tiles; xre_rij_xej_to_ei_v6.py:111-131).
+ * Zero in any field = kernel default.
+ */
+typedef struct fnsm_cfg {
+  int32_t variant;        /* kernel variant id within the class (0 = default)        */
+  int32_t tile_e;         /* elements per CTA tile                                   */
+  int32_t threads;        /* threads per CTA                                         */
+  int32_t stages;         /* depth of the global->shared pipeline                    */
+  int32_t ctas_per_sm;    /* persistent grid = ctas_per_sm * #SM (0 = kernel default)*/
+  int32_t reserved[3];
+} fnsm_cfg;
+
+/* one integer tunable and its legal range, for fnsm_b200_query_cfg_space */
+typedef struct fnsm_cfg_range {
+  char name[24];
+  int32_t lo, hi, step, dflt;
+} fnsm_cfg_range;
+
+/* kernel ids for fnsm_b200_query_cfg_space / DB "transform_id" column */
+enum {
+  FNSM_K_GENERIC = 0,
+  FNSM_K_GRAD = 1,
+  FNSM_K_DIV = 2,
+  FNSM_K_LIFT = 3,
+  FNSM_K_WAVE3D = 4,
+  FNSM_K_TENSOR_PRODUCT = 5
+};
+
+/* ------------------------------------------------------------------------
+ * Generic batched einsum: any BatchedEinsum, one thread per output entry,
+ * the reduction executed as a sequential odometer loop.  This is the CUDA
+ * form of the loop nest generate_loopy() emits with the *trivial* schedule
+ * (reference codegen/loopy.py:289-305) and exists so that every einsum the
+ * front-end accepts executes on the GPU; the classes below are the fast paths.
+ * ---------------------------------------------------------------------- */
+#define FNSM_MAX_INDICES 12
+#define FNSM_MAX_OPERANDS 6
+
+typedef struct fnsm_einsum_desc {
+  int32_t n_free;                         /* output rank; indices [0,n_free) are the output's, in order */
+  int32_t n_sum;                          /* contracted indices [n_free, n_free+n_sum)                  */
+  int32_t n_operands;
+  int32_t dtype;                          /* FNSM_F64 / FNSM_F32 (all operands and the output)          */
+  int64_t extent[FNSM_MAX_INDICES];       /* symbolic extents already bound                             */
+  int64_t out_stride[FNSM_MAX_INDICES];   /* element strides of the output per free index               */
+  int64_t in_stride[FNSM_MAX_OPERANDS][FNSM_MAX_INDICES]; /* 0 if the operand lacks the index; summed if it repeats */
+} fnsm_einsum_desc;
+
+/* replaces: executor launch of the untransformed kernel, measure.py:163-165.
+ * `inputs` = b rows x n_operands device pointers (row-major), `outputs` = b pointers. */
+int fnsm_b200_generic_einsum(const fnsm_einsum_desc* desc, int32_t b,
+                             const void* const* inputs, void* const* outputs,
+                             void* stream);
+
+/* ------------------------------------------------------------------------
+ * Operator-matrix x element-batch einsums (DG grad / div / face-mass lift).
+ * replaces: generate_loopy + tuning/impls/{xre_rij_ej_to_xei, xre_rij_xej_to_ei*,
+ * ifj_fe_fej_to_ei*, batched_*}.py + executor launch (measure.py:244-273).
+ *   kind      FNSM_OP_*
+ *   jac       geometric factors (J), op = constant operator (D / R / L)
+ *   fields    b device pointers u_k / v_k;  outs = b device pointers
+ *   n_outer   ndim (grad/div: extent of x and r) or nfaces (lift: extent of f)
+ *   n_i, n_j  output dofs per element, contracted dofs per element (35,35 / 35,15 for p=4 tets)
+ * ---------------------------------------------------------------------- */
+int fnsm_b200_opmat_batch(int32_t kind, int32_t dtype,
+                          const void* jac, const void* op,
+                          const void* const* fields, void* const* outs, int32_t b,
+                          int32_t n_outer, int32_t n_i, int32_t n_j,
+                          int64_t E, const fnsm_cfg* cfg, void* stream);
+
+/* ------------------------------------------------------------------------
+ * wave_3d_p4: div(v) + grad(u) + 4-field face-mass lift in ONE launch,
+ * sharing J and the resident operator matrices.
+ * replaces: the three autotuned kernels of examples/wave_3d_p4_auto.py:16-63.
+ * ---------------------------------------------------------------------- */
+typedef struct fnsm_wave_args {
+  const void* J;        /* (3,3,E)  */
+  const void* D;        /* (3,35,35) */
+  const void* v;        /* (3,E,35)  -> div_out  */
+  const void* u;        /* (E,35)    -> grad_out */
+  const void* L;        /* (35,4,15) */
+  const void* Jface;    /* (4,E)     */
+  const void* F[4];     /* (4,E,15) each */
+  void* div_out;        /* (E,35)   */
+  void* grad_out;       /* (3,E,35) */
+  void* lift_out[4];    /* (E,35) each */
+} fnsm_wave_args;
+
+int fnsm_b200_wave3d_fused(int32_t dtype, const fnsm_wave_args* args, int64_t E,
+                           const fnsm_cfg* cfg, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Tensor-product sum-factorisation on hexes: one 1-D operator applied along
+ * one of the three tensor directions,
+ *   mode 0: eabc,ia->eibc   mode 1: eabc,ib->eaic   mode 2: eabc,ic->eabi
+ * A and out are (E, n1d, n1d, n1d); M is (n1d, n1d) row-major M[i][a].
+ * (No transform exists for this in the reference)
+ * ---------------------------------------------------------------------- */
+int fnsm_b200_tensor_product(int32_t dtype, const void* A, const void* M, void* out,
+                             int32_t n1d, int32_t mode, int64_t E,
+                             const fnsm_cfg* cfg, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Tuning-space introspection (replaces the @transform_param declarations of a
+ * transform script, reference tuning/__init__.py:109-194).  Writes up to `cap`
+ * ranges, returns the number of tunables of the kernel (or a negative error).
+ * ---------------------------------------------------------------------- */
+int fnsm_b200_query_cfg_space(int32_t kernel_id, fnsm_cfg_range* out, int32_t cap);
+
+/* ------------------------------------------------------------------------
+ * Device peaks for the roofline (replaces the static table
+ * src/feinsum/data/device_info.py:4-28 with measurements on the running box).
+ *   which: 0 = FP64 FMA GFLOP/s, 1 = FP32 FMA GFLOP/s, 2 = HBM copy GB/s,
+ *          3 = FP64 DMMA (mma.sync m8n8k4) GFLOP/s
+ * Synchronous; runs a register-resident micro-kernel for a few milliseconds.
+ * ---------------------------------------------------------------------- */
+int fnsm_b200_measure_peak(int32_t which, double* result);
+
+/* strided 2-D copy helper for the host-buffer path (cudaMemcpy2DAsync):
+ * kind 0 = host->device, 1 = device->host.  Host memory should be pinned. */
+int fnsm_b200_copy2d_async(void* dst, int64_t dpitch, const void* src, int64_t spitch,
+                           int64_t width_bytes, int64_t height, int32_t kind, void* stream);
+
+/* number of kernel launches issued through this library since load (all threads) */
+int64_t fnsm_b200_launch_count(void);
+
+int fnsm_b200_abi_version(void);
+const char* fnsm_b200_strerror(int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FNSM_B200_H */

@@ -1,0 +1,68 @@
+"""measure.py on a real device: validation gate, CUDA-event timeit, roofline table."""
+
+import numpy as np
+import pytest
+
+import feinsum_b200 as f
+from feinsum_b200 import measure
+from tests import einsums as E
+
+pytestmark = pytest.mark.gpu
+
+IDENTITY = lambda t_unit, insn_match, kernel_name: t_unit  # noqa: E731  (reference tests' transform)
+
+
+@pytest.fixture(autouse=True)
+def short_timing(monkeypatch):
+    monkeypatch.setattr(measure, "N_MIN_SIM_SECS", 0.05)
+
+
+def test_timeit_reference_style(cq):
+    # reference test/test_codegen.py:34-120
+    for e in (E.div_components(), E.face_mass_se(), E.grad()):
+        t = measure.timeit(e, transform=IDENTITY, cq=cq, long_dim_length=300)
+        assert 0 < t < 1
+
+
+def test_simple_matvec(cq):
+    # reference test/test_measure.py:33-52
+    measure.timeit(E.matvec_f32(), transform=IDENTITY, cq=cq)
+    measure.timeit(E.matvec_f32(long=True), transform=IDENTITY, cq=cq)
+
+
+def test_pprint_roofline_comparison(cq):
+    # reference test/test_measure.py:55-81, with a launch-parameter transform
+    s = measure.stringify_comparison_vs_roofline(
+        E.grad(), cq=cq,
+        transform=lambda t_unit, insn_match, kernel_name: t_unit.with_params(variant=0, tile_e=32),
+        long_dim_length=500,
+    )
+    assert "Measured GOps/s" in s and "float64" in s
+
+
+def test_validation_gate_raises_on_wrong_kernel(cq):
+    from feinsum_b200.codegen.cuda import CudaProgram, KernelPlan
+
+    # force the div kernel onto the grad einsum's data layout -> wrong numbers
+    e = E.div()
+
+    def wrong(t_unit, insn_match=None, kernel_name=None):
+        return CudaProgram(t_unit.einsum, KernelPlan(
+            "lift_fe", (1, 0, 2), t_unit.plan.facts, "e"))
+
+    with pytest.raises((f.TransformValidationError, f.CudaBackendError)):
+        measure.validate_batched_einsum_transform(e, cq, wrong)
+
+
+def test_giga_op_rate_keys(cq):
+    r = measure.measure_giga_op_rate(E.div(), transform=IDENTITY, cq=cq, long_dim_length=2000)
+    assert set(r) == {np.dtype("float64")} and r[np.dtype("float64")] > 0
+
+
+def test_measured_peaks(cq):
+    from feinsum_b200 import _cabi
+
+    fp64 = _cabi.measure_peak(0)
+    assert 5_000 < fp64 < 100_000
+    bw = _cabi.measure_peak(2)
+    assert 1_000 < bw < 12_000

@@ -1,0 +1,229 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  GPU only."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+import feinsum_b200 as f
+from feinsum_b200.codegen import generate_cuda
+from oracle import np_oracle
+from tests import einsums as E
+from tests.test_oracle import CASES, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def run(einsum, host_inputs, cq, **params):
+    import torch
+
+    prog = generate_cuda(einsum)
+    if params:
+        prog = prog.with_params(**params)
+    dev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(cq.torch_device) for k, v in host_inputs.items()}
+    evt, outs = prog.executor(cq)(cq, **dev)
+    evt.wait()
+    return {k: v.cpu().numpy() for k, v in outs.items()}
+
+
+def check(einsum, n, cq, seed=0, **params):
+    ins = np_oracle.generate_input_arrays(einsum, n, seed)
+    got = run(einsum, ins, cq, **params)
+    fp32 = any(np.dtype(d) == np.float32 for d in einsum.arg_to_dtype.values())
+    ref = (np_oracle.reference_outputs_fp64 if fp32 else np_oracle.reference_outputs)(einsum, ins)
+    np_oracle.assert_matches(got, ref, north_star=True)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_fixtures(golden_dir, cq, name):
+    e, ins, outs, _ = load_case(golden_dir, name)
+    got = run(e, ins, cq)
+    np_oracle.assert_matches(got, outs, north_star=False)
+    np_oracle.assert_matches(got, outs, north_star=True)
+
+
+SIZES = [1, 2, 15, 16, 17, 100, 1001, 10007]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n", SIZES)
+def test_div_fp64(cq, n, variant):
+    check(E.div(), n, cq, variant=variant)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n", SIZES)
+def test_grad_fp64(cq, n, variant):
+    check(E.grad(), n, cq, variant=variant)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("builder", [E.lift_ef, E.lift_fe])
+def test_lift_fp64(cq, n, variant, builder):
+    check(builder(), n, cq, variant=variant)
+
+
+@pytest.mark.parametrize("n", [1, 17, 1001])
+@pytest.mark.parametrize("builder", [E.grad, E.div, E.lift_ef, E.lift_fe])
+def test_opmat_fp32(cq, n, builder):
+    check(builder(dtype="float32"), n, cq)
+
+
+@pytest.mark.parametrize("n", [1, 100])
+def test_grad_batched(cq, n):
+    check(E.grad_batched(3), n, cq)
+    check(E.grad_batched(9), n, cq)      # more rows than one launch group
+
+
+@pytest.mark.parametrize("ndof,ndim", [(4, 3), (10, 3), (20, 3), (6, 2), (15, 2)])
+def test_other_orders_take_the_simt_variant(cq, ndof, ndim):
+    check(E.grad(ndim=ndim, ndof=ndof), 101, cq)
+    check(E.div(ndim=ndim, ndof=ndof), 101, cq)
+
+
+def test_lift_other_orders(cq):
+    check(E.lift_ef(b=3, nface=4, nvol=20, nfd=10), 77, cq)
+    check(E.lift_fe(b=5, nface=3, nvol=10, nfd=4), 77, cq)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("n1d", [2, 3, 4, 7, 8])
+def test_tensor_product(cq, dtype, mode, n1d):
+    for n in (1, 33, 1000):
+        check(E.tensor_product(mode, n1d, dtype), n, cq)
+
+
+def test_tensor_product_persistent_grid(cq):
+    check(E.tensor_product(0, 8), 5000, cq, ctas_per_sm=2)
+
+
+@pytest.mark.parametrize("builder", [E.div_components, E.face_mass_se, E.matvec_f32])
+def test_reference_test_einsums_generic(cq, builder):
+    # reference test/test_codegen.py:34-97, test/test_measure.py:33-52 (E = 300)
+    check(builder(), 300, cq)
+
+
+def test_generic_misc(cq):
+    check(E.matvec_f32(long=True), 1000, cq)
+    e = f.einsum("iij,j->i", f.array("A", (5, 5, 7)), f.array("x", 7))
+    check(e, 1, cq)
+    e = f.einsum("ijk->ij", f.array("P", ("I", 72, 4)))   # reference tuning test einsum
+    check(e, 100, cq)
+    e = f.einsum("eij,ej->", f.array("A", ("E", 3, 4)), f.array("x", ("E", 4)))  # scalar output
+    check(e, 50, cq)
+
+
+def test_trivial_vs_optimal_schedule_agree(cq):
+    # reference test/test_codegen.py:123-165: generic kernel (trivial schedule) vs
+    # specialised kernel (hoisted) on the same inputs
+    import torch
+    from feinsum_b200.codegen.cuda import CudaProgram, KernelPlan
+
+    e = E.grad()
+    ins = np_oracle.generate_input_arrays(e, 5)
+    fast = run(e, ins, cq)
+    dev = {k: torch.from_numpy(v).to(cq.torch_device) for k, v in ins.items()}
+    generic = CudaProgram(e, KernelPlan("generic", (0, 1, 2), long_index="e"))
+    evt, outs = generic.executor(cq)(cq, **dev)
+    evt.wait()
+    np.testing.assert_allclose(outs["_fe_out"].cpu().numpy(), fast["_fe_out"], rtol=1e-12)
+
+
+def test_preallocated_outputs_and_errors(cq):
+    import torch
+
+    e = E.div()
+    ins = np_oracle.generate_input_arrays(e, 40)
+    dev = {k: torch.from_numpy(v).to(cq.torch_device) for k, v in ins.items()}
+    out = torch.zeros((40, 35), dtype=torch.float64, device=cq.torch_device)
+    ex = generate_cuda(e).executor(cq)
+    evt, outs = ex(cq, _fe_out=out, **dev)
+    evt.wait()
+    assert outs["_fe_out"] is out
+    np_oracle.assert_matches({"_fe_out": out.cpu().numpy()}, np_oracle.reference_outputs(e, ins))
+    with pytest.raises(ValueError):
+        ex(cq, _fe_out=torch.zeros((41, 35), dtype=torch.float64, device=cq.torch_device), **dev)
+    with pytest.raises(TypeError):
+        ex(cq, **{**dev, "J": ins["J"]})          # host array is not a device buffer
+    with pytest.raises(TypeError):
+        ex(cq, **{k: v for k, v in dev.items() if k != "u"})
+    with pytest.raises(ValueError):
+        ex(cq, **{**dev, "u": dev["u"][:, :39]})  # inconsistent E / non-contiguous
+    with pytest.raises(TypeError):
+        ex(cq, bogus=out, **dev)
+    with pytest.raises(f.InvalidParameterError):
+        generate_cuda(e).with_params(variant=7).executor(cq)(cq, **dev)
+
+
+def test_empty_batch(cq):
+    import torch
+
+    e = E.div()
+    dev = {
+        "J": torch.zeros((3, 3, 0), dtype=torch.float64, device=cq.torch_device),
+        "D": torch.zeros((3, 35, 35), dtype=torch.float64, device=cq.torch_device),
+        "u": torch.zeros((3, 0, 35), dtype=torch.float64, device=cq.torch_device),
+    }
+    evt, outs = generate_cuda(e).executor(cq)(cq, **dev)
+    evt.wait()
+    assert tuple(outs["_fe_out"].shape) == (0, 35)
+
+
+def test_unaligned_views_take_the_plain_load_path(cq):
+    # element count odd AND base pointers offset by 8 bytes: TMA path must not be taken
+    import torch
+
+    e = E.div()
+    n = 1001
+    ins = np_oracle.generate_input_arrays(e, n)
+    dev = {}
+    for k, v in ins.items():
+        buf = torch.empty(v.size + 1, dtype=torch.float64, device=cq.torch_device)
+        view = buf[1:].view(v.shape)
+        view.copy_(torch.from_numpy(v))
+        dev[k] = view
+    evt, outs = generate_cuda(e).executor(cq)(cq, **dev)
+    evt.wait()
+    np_oracle.assert_matches({"_fe_out": outs["_fe_out"].cpu().numpy()}, np_oracle.reference_outputs(e, ins))
+
+
+def test_full_size_div_properties(cq):
+    """BASELINE config 2 size (E = 4M): per-element independence lets the oracle
+    check slices; linearity in u checks the whole array."""
+    import torch
+
+    e = E.div()
+    n = 4_000_000
+    g = torch.Generator(device=cq.torch_device).manual_seed(1)
+    J = torch.rand((3, 3, n), dtype=torch.float64, device=cq.torch_device, generator=g)
+    D = torch.rand((3, 35, 35), dtype=torch.float64, device=cq.torch_device, generator=g)
+    u = torch.rand((3, n, 35), dtype=torch.float64, device=cq.torch_device, generator=g)
+    ex = generate_cuda(e).executor(cq)
+    evt, o1 = ex(cq, J=J, D=D, u=u)
+    evt.wait()
+    out = o1["_fe_out"]
+    for sl in (slice(0, 64), slice(1_999_983, 2_000_047), slice(n - 64, n)):
+        ins = {"J": J[:, :, sl].cpu().numpy().copy(), "D": D.cpu().numpy(),
+               "u": u[:, sl, :].cpu().numpy().copy()}
+        np_oracle.assert_matches({"_fe_out": out[sl].cpu().numpy()},
+                                 np_oracle.reference_outputs(e, ins))
+    # linearity: div(J, D, 2u) == 2 div(J, D, u) exactly (power-of-two scaling)
+    evt, o2 = ex(cq, J=J, D=D, u=u * 2.0)
+    evt.wait()
+    assert torch.equal(o2["_fe_out"], out * 2.0)
+    # variant cross-check on the full array (simt vs dmma)
+    evt, o3 = generate_cuda(e).with_params(variant=0).executor(cq)(cq, J=J, D=D, u=u)
+    evt.wait()
+    rel = ((o3["_fe_out"] - out).abs().max() / out.abs().max()).item()
+    assert rel < 1e-13
+
+
+def test_launches_are_counted_and_native(cq):
+    from feinsum_b200 import _cabi
+
+    before = _cabi.launch_count()
+    check(E.div(), 64, cq)
+    assert _cabi.launch_count() > before
