@@ -164,6 +164,19 @@ def generate_c(einsum: Any, schedule: Any | None = None) -> str:
     return "\n".join(lines) + "\n"
 
 
+def _cpu_signature() -> str:
+    """-march=native objects are only valid on the CPU model that built them
+    (build container and GPU box differ), so the cache key carries the flags line."""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("flags"):
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown-cpu"
+
+
 class CKernel:
     """gcc-compiled loop nest for one (einsum, schedule)."""
 
@@ -174,7 +187,9 @@ class CKernel:
         flags = ["-O3", "-ffast-math", "-march=native", "-fPIC", "-shared"]
         if threads:
             flags.append("-fopenmp")
-        key = hashlib.sha1((self.source + " ".join(flags)).encode()).hexdigest()[:16]
+        key = hashlib.sha1(
+            (self.source + " ".join(flags) + _cpu_signature()).encode()
+        ).hexdigest()[:16]
         os.makedirs(_BUILD_DIR, exist_ok=True)
         so = os.path.join(_BUILD_DIR, f"fe_{key}.so")
         if not os.path.exists(so):
