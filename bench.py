@@ -161,7 +161,9 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="div_p4", choices=sorted(WORKLOADS))
     ap.add_argument("--elements", type=int, default=0, help="elements per GPU (default: workload's)")
-    ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 dmma, 2 simt")
+    ap.add_argument("--param", action="append", default=[], metavar="K=V",
+                    help="launch parameter of the kernel (threads=384, ...); may repeat")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -236,8 +238,10 @@ def main() -> None:
     dev = cq.torch_device
 
     prog = generate_cuda(einsum)
-    if args.variant >= 0:
+    if args.variant > 0:
         prog = prog.with_params(variant=args.variant)
+    if args.param:
+        prog = prog.with_params(**{k: int(v) for k, v in (kv.split("=") for kv in args.param)})
     ex = prog.executor(cq)
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)

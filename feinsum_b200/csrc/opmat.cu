@@ -23,11 +23,11 @@ int opmat_cfg_space(int kernel_id, fnsm_cfg_range* out, int cap) {
   (void)kernel_id;
   fnsm_cfg_range tmp[5];
   int n = 0;
-  set_range(&tmp[n++], "variant", 0, 1, 1, 1);        // 0 = simt, 1 = dmma (fp64, tuned shapes)
+  set_range(&tmp[n++], "variant", 0, 2, 1, 0);        // 0 = auto, 1 = dmma (fp64, p=4 shapes), 2 = simt
   set_range(&tmp[n++], "tile_e", 8, 64, 8, 16);        // simt: elements per CTA tile
   set_range(&tmp[n++], "ctas_per_sm", 1, 8, 1, 0);     // persistent grid size
-  set_range(&tmp[n++], "threads", 64, 512, 32, 0);     // dmma: 32*(consumer warps)+32
-  set_range(&tmp[n++], "stages", 2, 16, 1, 0);         // dmma: ring slots beyond one per warp
+  set_range(&tmp[n++], "threads", 128, 384, 64, 256);  // dmma: 32 * warps per persistent CTA (4, 8, 10, 12)
+  set_range(&tmp[n++], "stages", 0, 1, 1, 1);          // dmma: shared-memory slots per warp
   for (int i = 0; i < n && i < cap; ++i) out[i] = tmp[i];
   return n;
 }
@@ -77,11 +77,11 @@ static int opmat_dispatch(int kind, int dtype, const void* jac, const void* op,
                           cudaStream_t st) {
   DevInfo di;
   if (int rc = device_info(&di)) return rc;
-  int variant = cfg ? cfg->variant : -1;   // -1: library default
-  if (variant < -1 || variant > 1) return FNSM_E_BAD_CONFIG;
+  int variant = cfg ? cfg->variant : 0;    // 0: library default
+  if (variant < 0 || variant > 2) return FNSM_E_BAD_CONFIG;
   const bool dmma_ok = dtype == FNSM_F64 && dmma_supported(kind, n_outer, ni, nj);
   if (variant == 1 && !dmma_ok) return FNSM_E_UNSUPPORTED;
-  if (variant == -1) variant = dmma_ok ? 1 : 0;
+  if (variant == 0) variant = dmma_ok ? 1 : 2;
   for (int r0 = 0; r0 < b; r0 += 8) {
     const int nr = (b - r0 < 8) ? (b - r0) : 8;
     OpmatRows rows{};
@@ -131,9 +131,9 @@ extern "C" int fnsm_b200_wave3d_fused(int32_t dtype, const fnsm_wave_args* a, in
   DevInfo di;
   if (int rc = device_info(&di)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == FNSM_F64 && (!cfg || cfg->variant != 0))
+  if (dtype == FNSM_F64 && (!cfg || cfg->variant != 2))
     return launch_wave3d_dmma(a, E, cfg, di, st);
-  // variant 0 / fp32: three back-to-back launches of the simt kernels on one stream
+  // variant 2 / fp32: three back-to-back launches of the simt kernels on one stream
   const void* f1[1] = {a->v}; void* o1[1] = {a->div_out};
   int rc = opmat_dispatch(FNSM_OP_DIV, dtype, a->J, a->D, f1, o1, 1, 3, 35, 35, E, cfg, st);
   if (rc) return rc;

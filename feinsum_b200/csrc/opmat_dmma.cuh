@@ -1,28 +1,33 @@
 // Variant 1 ("dmma") of the DG operator kernels for fp64, p = 4 tets.
 //
 // Every DG einsum is (tiny per-element scaling) o (constant matrix x element
-// vector) -- SURVEY.md Appendix C.  Here the constant-matrix part runs on the
-// FP64 tensor path (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no
-// FP64 kind), with
-//     M = 8 elements,   N = 8 output dofs (or (r, dof) pairs),   K = 4 contracted dofs
-//   * B fragments (the operator, zero padded to multiples of 8 x 4) are laid
-//     out once per CTA in shared memory in fragment order [k-tile][n-tile][lane]
-//     -> conflict-free LDS.64, shared by the ME = 2 element tiles a warp owns;
-//   * A fragments (per-element data) are produced on the fly from the element
-//     slot: div folds the Jacobian (w = sum_x J[x,r,e] u[x,e,j]), lift scales
-//     by the face Jacobian, grad reads u directly and applies J to the
-//     accumulator fragments afterwards -- the hoisting the reference's
-//     transforms perform (tuning/impls/xre_rij_ej_to_xei.py:104-117,
-//     xre_rij_xej_to_ei_v6.py:212-248, ifj_fe_fej_to_ei_v3.py:94-105);
-//   * one persistent CTA per SM: NW consumer warps + 1 producer warp.  The
-//     producer streams 16-element chunks into a ring of shared-memory slots
-//     with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); a
-//     consumer warp owns one chunk at a time, so there is no CTA-wide barrier
-//     in steady state;
-//   * elements are permuted inside a 16-chunk (el = 4*(g&3) + (g>>2) + 2m) so
-//     that the stride-35 rows read by a half-warp fall into distinct banks.
+// vector) -- SURVEY.md Appendix C.  The constant-matrix part runs on the FP64
+// tensor path (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no FP64
+// kind) with   M = 8 elements,  N = 8 output columns,  K = 4 contracted dofs.
 //
-// Unaligned inputs (odd E, tail chunk) take a plain-load path in the producer.
+// Structure of all three kernels ("load -> registers -> release -> DMMA stream"):
+//   * one persistent CTA per SM, NW warps, NO producer warp and no CTA-wide
+//     barrier in steady state.  Every warp owns one private shared-memory slot
+//     and one mbarrier.  It waits for its slot, turns the slot into A fragments
+//     held in registers (div folds the Jacobian, w = sum_x J[x,r,e] u[x,e,j];
+//     lift scales by the face Jacobian; grad keeps u and applies J to the
+//     accumulators afterwards -- the hoisting the reference's transforms do,
+//     tuning/impls/xre_rij_ej_to_xei.py:104-117, xre_rij_xej_to_ei_v6.py:212-248,
+//     ifj_fe_fej_to_ei_v3.py:94-105), and immediately re-arms the slot with the
+//     1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of its NEXT
+//     work item, which then land while the warp issues its DMMAs.  Since only
+//     the owning warp ever waits on a slot's barrier, phases cannot alias.
+//   * B fragments (the operator, zero padded in K to multiples of 4) sit in
+//     shared memory in fragment order [tile][lane] -> conflict-free LDS.64,
+//     each shared by the ME = 2 element tiles of a 16-element chunk.
+//   * N = 35 output dofs are NOT padded to 40: dofs 0..31 take 4 DMMA column
+//     tiles, dofs 32..34 are accumulated with DFMA from the same A registers
+//     (each lane owns the k = t (mod 4) partial sums; two shuffles reduce).
+//     That removes the 12.5 % padding waste of a fifth column tile.
+//   * elements are permuted inside a chunk (el = 4*(g&3) + (g>>2) + 2m) so the
+//     stride-35 / stride-15 rows read by a half-warp fall into distinct banks.
+//
+// Unaligned inputs (odd E, misaligned base, tail chunk) take a plain-load path.
 #pragma once
 #include "common.cuh"
 #include "opmat_simt.cuh"
@@ -56,248 +61,345 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE_%=:\n\t}"
       :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// orders this thread's earlier generic-proxy accesses to shared memory before
+// later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier (TMA unit)
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// 1-D bulk copy shared -> global (TMA unit), tracked by the bulk async-group of the issuing thread
+__device__ __forceinline__ void tma_store_1d(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all earlier bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 lanes sharing g
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+// warp index as a value ptxas can prove warp-uniform (keeps TMA operands in uniform registers)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// one elected lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 // ------------------------------------------------------------ geometry -----
-constexpr int kME = 2;            // element tiles (of 8) per warp chunk
-constexpr int kCH = 8 * kME;      // elements per chunk / ring slot
-constexpr int kMaxWarps = 12;
-
-struct DmmaShape {
-  // p = 4 tets
-  static constexpr int NI = 35, NJ = 35, ND = 3, NF = 4, NFJ = 15;
-  static constexpr int NT = 5;                 // n-tiles of 8 covering NI (padded to 40)
-};
+constexpr int kME = 2;            // element tiles (of 8) per chunk
+constexpr int kCH = 8 * kME;      // elements per chunk / slot
+constexpr int kNT = 4;            // DMMA column tiles: dofs 0..31
+constexpr int kNL = 3;            // left-over dofs 32..34 (DFMA)
 
 __device__ __forceinline__ int chunk_el(int g, int m) { return 4 * (g & 3) + (g >> 2) + 2 * m; }
 
+constexpr int OUT_BLOCK = kCH * 35;   // doubles of one [16 elements][35 dofs] output block
+
+// Flush one staged [kCH][35] block to out[e0 .. e0+kCH) (row length 35, contiguous):
+// one TMA bulk store when aligned and complete, coalesced plain stores otherwise.
+// Call with the whole warp after __syncwarp() made the staged values visible.
+__device__ __forceinline__ void flush_block(double* __restrict__ dst, const double* stage, long long e0,
+                                            long long E, bool tma_ok, int lane) {
+  if (tma_ok && e0 + kCH <= E) {
+    if (elect_one()) tma_store_1d(dst, stage, OUT_BLOCK * 8);
+  } else {
+    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+    for (int k = lane; k < ne * 35; k += 32) dst[k] = stage[k];
+  }
+}
+
+// De-synchronise the warps of a CTA once at start-up (warp w waits w * cycles):
+// all warps run the same phases (slot -> registers, DMMA stream, stage + store);
+// in lock-step the non-DMMA phases of every warp coincide and the FP64 pipe idles.
+__device__ __forceinline__ void stagger_start(int cycles, int warp) {
+  if (cycles > 0) {
+    const long long t0 = clock64(), wait = (long long)cycles * warp;
+    while (clock64() - t0 < wait) {}
+  }
+}
+
+struct WorkIter {
+  long long item, stride, nitems;
+};
+__device__ __forceinline__ WorkIter work_iter(int nw, long long nitems) {
+  WorkIter w;
+  w.item = (long long)blockIdx.x * nw + uniform_warp_idx();
+  w.stride = (long long)gridDim.x * nw;
+  w.nitems = nitems;
+  return w;
+}
+
 // ================================================================= DIV =====
-// out[e,i] = sum_{r,j} D[r,i,j] * (sum_x J[x,r,e] u[x,e,j])
+// out[e,i] = sum_{r,j} D[r,i,j] * w[r,e,j],   w[r,e,j] = sum_x J[x,r,e] u[x,e,j]
 // k-tiles ordered (jq, r): kt = 3*jq + r, k-in-tile t <-> j = 4*jq + t
 struct DivLayout {
   static constexpr int KT = 27;
-  static constexpr int B_DOUBLES = KT * DmmaShape::NT * 32;          // 4320
+  static constexpr int B_MAIN = KT * kNT * 32;                       // 3456
+  static constexpr int B_LEFT = KT * 4 * 4;                          // [kt][t][3 dofs + pad]
+  static constexpr int B_DOUBLES = B_MAIN + B_LEFT;                  // 3888
   static constexpr int U_SLAB = kCH * 35;                            // doubles per x
   static constexpr int SLOT_DOUBLES = 3 * U_SLAB + 9 * kCH;          // 1824 -> 14592 B
   static constexpr uint32_t SLOT_BYTES = SLOT_DOUBLES * 8;
 };
 
+__device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const double* __restrict__ Jg,
+                                          const double* __restrict__ ug, long long chunk, long long E,
+                                          bool tma_ok, int lane) {
+  using L = DivLayout;
+  const long long e0 = chunk * kCH;
+  if (tma_ok && e0 + kCH <= E) {
+    if (elect_one()) {
+      fence_proxy_async();
+      mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
+      for (int x = 0; x < 3; ++x)
+        tma_load_1d(s + x * L::U_SLAB, ug + ((long long)x * E + e0) * 35, L::U_SLAB * 8, bar);
+      for (int xr = 0; xr < 9; ++xr)
+        tma_load_1d(s + 3 * L::U_SLAB + xr * kCH, Jg + (long long)xr * E + e0, kCH * 8, bar);
+    }
+  } else {
+    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+    for (int x = 0; x < 3; ++x)
+      for (int k = lane; k < L::U_SLAB; k += 32)
+        s[x * L::U_SLAB + k] = (k < ne * 35) ? ug[((long long)x * E + e0) * 35 + k] : 0.0;
+    for (int k = lane; k < 9 * kCH; k += 32) {
+      const int xr = k / kCH, el = k - xr * kCH;
+      s[3 * L::U_SLAB + k] = (el < ne) ? Jg[(long long)xr * E + e0 + el] : 0.0;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+  }
+}
+
 template <int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, 1)
+__global__ void __launch_bounds__(NW * 32, 1)
 k_div_dmma(const double* __restrict__ Jg, const double* __restrict__ Dg,
            const double* __restrict__ ug, double* __restrict__ outg,
-           long long E, int nslots, int tma_ok) {
+           long long E, int tma_ok, int stagger) {
   using L = DivLayout;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sB = reinterpret_cast<double*>(smem_raw);
-  double* ring = sB + L::B_DOUBLES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)nslots * L::SLOT_DOUBLES);
-  uint64_t* empty = full + nslots;
+  double* sL = sB + L::B_MAIN;
+  double* slots = sB + L::B_DOUBLES;
+  double* stages = slots + (size_t)NW * L::SLOT_DOUBLES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * OUT_BLOCK);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // operator fragments: sB[(kt*NT + nt)*32 + lane] = D[r][8nt+g][4jq+t]
-  for (int idx = threadIdx.x; idx < L::B_DOUBLES; idx += blockDim.x) {
-    const int ln = idx & 31, nt = (idx >> 5) % DmmaShape::NT, kt = (idx >> 5) / DmmaShape::NT;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  // main operator fragments: sB[(kt*4 + nt)*32 + lane] = D[r][8nt+g][4jq+t]
+  for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
+    const int ln = idx & 31, nt = (idx >> 5) % kNT, kt = (idx >> 5) / kNT;
     const int g = ln >> 2, t = ln & 3, jq = kt / 3, r = kt - 3 * jq;
     const int i = 8 * nt + g, j = 4 * jq + t;
-    sB[idx] = (i < 35 && j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
+    sB[idx] = (j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
+  }
+  // left-over dofs: sL[(kt*4 + t)*4 + d] = D[r][32+d][4jq+t]
+  for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
+    const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
+    const int jq = kt / 3, r = kt - 3 * jq, j = 4 * jq + t;
+    sL[idx] = (d < kNL && j < 35) ? Dg[(r * 35 + 32 + d) * 35 + j] : 0.0;
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nslots; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
     mbar_fence_init();
   }
   __syncthreads();
 
+  double* s = slots + (size_t)warp * L::SLOT_DOUBLES;
+  double* stage = stages + (size_t)warp * OUT_BLOCK;
+  uint64_t* bar = &bars[warp];
+  const double* sJ = s + 3 * L::U_SLAB;
   const long long nchunks = (E + kCH - 1) / kCH;
-  const long long G = gridDim.x;
-  // number of chunks this CTA processes: b, b+G, ...
-  const long long nq = (nchunks > (long long)blockIdx.x) ? (nchunks - blockIdx.x + G - 1) / G : 0;
-
-  if (warp == NW) {
-    // ------------------------------------------------------ producer ------
-    for (long long q = 0; q < nq; ++q) {
-      const int slot = (int)(q % nslots);
-      const long long use = q / nslots;
-      if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
-      const long long e0 = (blockIdx.x + q * G) * kCH;
-      double* s = ring + (size_t)slot * L::SLOT_DOUBLES;
-      if (tma_ok && e0 + kCH <= E) {
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&full[slot], L::SLOT_BYTES);
-          for (int x = 0; x < 3; ++x)
-            tma_load_1d(s + x * L::U_SLAB, ug + ((long long)x * E + e0) * 35, L::U_SLAB * 8, &full[slot]);
-          for (int xr = 0; xr < 9; ++xr)
-            tma_load_1d(s + 3 * L::U_SLAB + xr * kCH, Jg + (long long)xr * E + e0, kCH * 8, &full[slot]);
-        }
-      } else {
-        const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-        for (int x = 0; x < 3; ++x)
-          for (int k = lane; k < L::U_SLAB; k += 32)
-            s[x * L::U_SLAB + k] = (k < ne * 35) ? ug[((long long)x * E + e0) * 35 + k] : 0.0;
-        for (int k = lane; k < 9 * kCH; k += 32) {
-          const int xr = k / kCH, el = k - xr * kCH;
-          s[3 * L::U_SLAB + k] = (el < ne) ? Jg[(long long)xr * E + e0 + el] : 0.0;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[slot]);
-      }
-    }
-    return;
-  }
-
-  // -------------------------------------------------------- consumers -----
+  WorkIter wi = work_iter(NW, nchunks);
   const int g = lane >> 2, t = lane & 3;
-  for (long long q = warp; q < nq; q += NW) {
-    const int slot = (int)(q % nslots);
-    const long long use = q / nslots;
-    mbar_wait(&full[slot], (uint32_t)(use & 1));
-    const double* s = ring + (size_t)slot * L::SLOT_DOUBLES;
-    const double* sJ = s + 3 * L::U_SLAB;
 
-    double acc[kME][DmmaShape::NT][2];
-    double Jr[kME][9];
+  const bool dbg_noload = tma_ok & 2, dbg_nostore = tma_ok & 4;   // profiling aids (results invalid)
+  tma_ok &= 1;
+  if (wi.item < wi.nitems && !dbg_noload) div_issue(s, bar, Jg, ug, wi.item, E, tma_ok, lane);
+  stagger_start(stagger, warp);
+  for (uint32_t n = 0; wi.item < wi.nitems; wi.item += wi.stride, ++n) {
+    if (!dbg_noload) mbar_wait(bar, n & 1u);
+    // ---- slot -> A fragments (Jacobian folded in) ----
+    double a[kME][L::KT];
 #pragma unroll
     for (int m = 0; m < kME; ++m) {
       const int el = chunk_el(g, m);
+      double Jr[9];
 #pragma unroll
-      for (int xr = 0; xr < 9; ++xr) Jr[m][xr] = sJ[xr * kCH + el];
+      for (int xr = 0; xr < 9; ++xr) Jr[xr] = sJ[xr * kCH + el];
 #pragma unroll
-      for (int nt = 0; nt < DmmaShape::NT; ++nt) { acc[m][nt][0] = 0.0; acc[m][nt][1] = 0.0; }
-    }
-#pragma unroll
-    for (int jq = 0; jq < 9; ++jq) {
-      double ux[kME][3];
-#pragma unroll
-      for (int m = 0; m < kME; ++m) {
-        const int el = chunk_el(g, m);
+      for (int jq = 0; jq < 9; ++jq) {
+        double ux[3];
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
           double v = s[x * L::U_SLAB + el * 35 + 4 * jq + t];
           if (jq == 8 && t == 3) v = 0.0;           // j = 35 is padding
-          ux[m][x] = v;
+          ux[x] = v;
         }
-      }
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        double a[kME];
-#pragma unroll
-        for (int m = 0; m < kME; ++m)
-          a[m] = fma(Jr[m][6 + r], ux[m][2], fma(Jr[m][3 + r], ux[m][1], Jr[m][r] * ux[m][0]));
-        const double* bp = sB + ((3 * jq + r) * DmmaShape::NT) * 32 + lane;
-#pragma unroll
-        for (int nt = 0; nt < DmmaShape::NT; ++nt) {
-          const double b = bp[nt * 32];
-#pragma unroll
-          for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m], b);
-        }
+        for (int r = 0; r < 3; ++r)
+          a[m][3 * jq + r] = fma(Jr[6 + r], ux[2], fma(Jr[3 + r], ux[1], Jr[r] * ux[0]));
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[slot]);     // slot data no longer needed
+    __syncwarp();                                  // every lane is done reading the slot
+    if (wi.item + wi.stride < wi.nitems && !dbg_noload) div_issue(s, bar, Jg, ug, wi.item + wi.stride, E, tma_ok, lane);
 
-    const long long e0 = (blockIdx.x + q * G) * kCH;
+    // ---- DMMA stream ----
+    double acc[kME][kNT][2];
+    double accL[2][kME][kNL];      // two partial sums per value: DFMA latency >> 6 chains
 #pragma unroll
     for (int m = 0; m < kME; ++m) {
-      const long long e = e0 + chunk_el(g, m);
-      if (e < E) {
-        double* o = outg + e * 35;
 #pragma unroll
-        for (int nt = 0; nt < DmmaShape::NT; ++nt) {
-          const int i = 8 * nt + 2 * t;
-          if (i < 35) stg_stream(o + i, acc[m][nt][0]);
-          if (i + 1 < 35) stg_stream(o + i + 1, acc[m][nt][1]);
-        }
+      for (int nt = 0; nt < kNT; ++nt) { acc[m][nt][0] = 0.0; acc[m][nt][1] = 0.0; }
+#pragma unroll
+      for (int d = 0; d < kNL; ++d) { accL[0][m][d] = 0.0; accL[1][m][d] = 0.0; }
+    }
+#pragma unroll
+    for (int kt = 0; kt < L::KT; ++kt) {
+      const double* bp = sB + (kt * kNT) * 32 + lane;
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt) {
+        const double b = bp[nt * 32];
+#pragma unroll
+        for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m][kt], b);
+      }
+      const double2 l01 = *reinterpret_cast<const double2*>(sL + (kt * 4 + t) * 4);
+      const double l2 = sL[(kt * 4 + t) * 4 + 2];
+#pragma unroll
+      for (int m = 0; m < kME; ++m) {
+        accL[kt & 1][m][0] = fma(a[m][kt], l01.x, accL[kt & 1][m][0]);
+        accL[kt & 1][m][1] = fma(a[m][kt], l01.y, accL[kt & 1][m][1]);
+        accL[kt & 1][m][2] = fma(a[m][kt], l2, accL[kt & 1][m][2]);
       }
     }
+    // ---- stage the [16][35] block, then one bulk store ----
+    const long long e0 = wi.item * kCH;
+    if (lane == 0) tma_store_wait_read();          // previous block has left the stage
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < kME; ++m) {
+      double* o = stage + chunk_el(g, m) * 35;
+      const double l0 = quad_sum(accL[0][m][0] + accL[1][m][0]), l1 = quad_sum(accL[0][m][1] + accL[1][m][1]),
+                   l2 = quad_sum(accL[0][m][2] + accL[1][m][2]);
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt) {
+        o[8 * nt + 2 * t] = acc[m][nt][0];
+        o[8 * nt + 2 * t + 1] = acc[m][nt][1];
+      }
+      if (t < kNL) o[32 + t] = t == 0 ? l0 : (t == 1 ? l1 : l2);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (!dbg_nostore) {
+      flush_block(outg + e0 * 35, stage, e0, E, tma_ok, lane);
+      if (lane == 0) tma_store_commit();
+    }
   }
+  if (lane == 0) tma_store_wait_all();
 }
 
 // ================================================================ GRAD =====
 // T[r][e][i] = sum_j D[r,i,j] u[e,j];  out[x,e,i] = sum_r J[x,r,e] T[r][e][i]
-// n-tiles ordered (it, r); k-tiles kt <-> j = 4*kt + t (9 tiles)
+// k-tiles kt <-> j = 4*kt + t (9 tiles).  Column tiles: group G (8 dofs) x 3
+// tiles; tile jt, column c <-> value v = 2*jt + (c&1) of lane t = c>>1, which is
+// (dof 8G + 2t + v/3, r = v%3): a lane ends up with all three r of its two dofs,
+// so J is applied in registers.
 struct GradLayout {
   static constexpr int KT = 9;
-  static constexpr int B_DOUBLES = DmmaShape::NT * KT * 3 * 32;       // 4320
+  static constexpr int NG = 4;
+  static constexpr int B_MAIN = NG * KT * 3 * 32;                     // 3456
+  static constexpr int L_STRIDE = 10;                                 // 9 columns (dof-major, r minor) + pad
+  static constexpr int B_LEFT = KT * 4 * L_STRIDE;                    // 360
+  static constexpr int B_DOUBLES = B_MAIN + B_LEFT;
   static constexpr int U_SLAB = kCH * 35;
   static constexpr int SLOT_DOUBLES = U_SLAB + 9 * kCH;               // 704 -> 5632 B
   static constexpr uint32_t SLOT_BYTES = SLOT_DOUBLES * 8;
 };
 
+__device__ __forceinline__ void grad_issue(double* s, uint64_t* bar, const double* __restrict__ Jg,
+                                           const double* __restrict__ ug, long long chunk, long long E,
+                                           bool tma_ok, int lane) {
+  using L = GradLayout;
+  const long long e0 = chunk * kCH;
+  if (tma_ok && e0 + kCH <= E) {
+    if (elect_one()) {
+      fence_proxy_async();
+      mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
+      tma_load_1d(s, ug + e0 * 35, L::U_SLAB * 8, bar);
+      for (int xr = 0; xr < 9; ++xr)
+        tma_load_1d(s + L::U_SLAB + xr * kCH, Jg + (long long)xr * E + e0, kCH * 8, bar);
+    }
+  } else {
+    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+    for (int k = lane; k < L::U_SLAB; k += 32) s[k] = (k < ne * 35) ? ug[e0 * 35 + k] : 0.0;
+    for (int k = lane; k < 9 * kCH; k += 32) {
+      const int xr = k / kCH, el = k - xr * kCH;
+      s[L::U_SLAB + k] = (el < ne) ? Jg[(long long)xr * E + e0 + el] : 0.0;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+  }
+}
+
 template <int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, 1)
+__global__ void __launch_bounds__(NW * 32, 1)
 k_grad_dmma(const double* __restrict__ Jg, const double* __restrict__ Dg,
             const double* __restrict__ ug, double* __restrict__ outg,
-            long long E, int nslots, int tma_ok) {
+            long long E, int tma_ok, int stagger) {
   using L = GradLayout;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sB = reinterpret_cast<double*>(smem_raw);
-  double* ring = sB + L::B_DOUBLES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)nslots * L::SLOT_DOUBLES);
-  uint64_t* empty = full + nslots;
+  double* sL = sB + L::B_MAIN;
+  double* slots = sB + L::B_DOUBLES;
+  double* stages = slots + (size_t)NW * L::SLOT_DOUBLES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * 3 * OUT_BLOCK);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // sB[((it*KT + kt)*3 + r)*32 + lane] = D[r][8it+g][4kt+t]
-  for (int idx = threadIdx.x; idx < L::B_DOUBLES; idx += blockDim.x) {
-    const int ln = idx & 31, r = (idx >> 5) % 3, kt = ((idx >> 5) / 3) % L::KT, it = (idx >> 5) / (3 * L::KT);
-    const int g = ln >> 2, t = ln & 3;
-    const int i = 8 * it + g, j = 4 * kt + t;
-    sB[idx] = (i < 35 && j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  // sB[((G*KT + kt)*3 + jt)*32 + lane]: column c = g of tile jt
+  for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
+    const int ln = idx & 31, jt = (idx >> 5) % 3, kt = ((idx >> 5) / 3) % L::KT, G = (idx >> 5) / (3 * L::KT);
+    const int c = ln >> 2, t = ln & 3;
+    const int v = 2 * jt + (c & 1);
+    const int i = 8 * G + 2 * (c >> 1) + v / 3, r = v % 3, j = 4 * kt + t;
+    sB[idx] = (j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
+  }
+  // sL[(kt*4 + t)*10 + 3*d + r] = D[r][32+d][4kt+t]
+  for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
+    const int col = idx % L::L_STRIDE, t = (idx / L::L_STRIDE) & 3, kt = idx / (4 * L::L_STRIDE);
+    const int d = col / 3, r = col - 3 * d, j = 4 * kt + t;
+    sL[idx] = (col < 9 && j < 35) ? Dg[(r * 35 + 32 + d) * 35 + j] : 0.0;
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nslots; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
     mbar_fence_init();
   }
   __syncthreads();
 
+  double* s = slots + (size_t)warp * L::SLOT_DOUBLES;
+  double* stage = stages + (size_t)warp * 3 * OUT_BLOCK;      // [x][16][35]
+  uint64_t* bar = &bars[warp];
+  const double* sJ = s + L::U_SLAB;
   const long long nchunks = (E + kCH - 1) / kCH;
-  const long long G = gridDim.x;
-  const long long nq = (nchunks > (long long)blockIdx.x) ? (nchunks - blockIdx.x + G - 1) / G : 0;
-
-  if (warp == NW) {
-    for (long long q = 0; q < nq; ++q) {
-      const int slot = (int)(q % nslots);
-      const long long use = q / nslots;
-      if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
-      const long long e0 = (blockIdx.x + q * G) * kCH;
-      double* s = ring + (size_t)slot * L::SLOT_DOUBLES;
-      if (tma_ok && e0 + kCH <= E) {
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&full[slot], L::SLOT_BYTES);
-          tma_load_1d(s, ug + e0 * 35, L::U_SLAB * 8, &full[slot]);
-          for (int xr = 0; xr < 9; ++xr)
-            tma_load_1d(s + L::U_SLAB + xr * kCH, Jg + (long long)xr * E + e0, kCH * 8, &full[slot]);
-        }
-      } else {
-        const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-        for (int k = lane; k < L::U_SLAB; k += 32) s[k] = (k < ne * 35) ? ug[e0 * 35 + k] : 0.0;
-        for (int k = lane; k < 9 * kCH; k += 32) {
-          const int xr = k / kCH, el = k - xr * kCH;
-          s[L::U_SLAB + k] = (el < ne) ? Jg[(long long)xr * E + e0 + el] : 0.0;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[slot]);
-      }
-    }
-    return;
-  }
-
+  WorkIter wi = work_iter(NW, nchunks);
   const int g = lane >> 2, t = lane & 3;
-  for (long long q = warp; q < nq; q += NW) {
-    const int slot = (int)(q % nslots);
-    const long long use = q / nslots;
-    mbar_wait(&full[slot], (uint32_t)(use & 1));
-    const double* s = ring + (size_t)slot * L::SLOT_DOUBLES;
-    const double* sJ = s + L::U_SLAB;
 
+  if (wi.item < wi.nitems) grad_issue(s, bar, Jg, ug, wi.item, E, tma_ok, lane);
+  stagger_start(stagger, warp);
+  for (uint32_t n = 0; wi.item < wi.nitems; wi.item += wi.stride, ++n) {
+    mbar_wait(bar, n & 1u);
     double a[kME][L::KT];
     double Jr[kME][9];
 #pragma unroll
@@ -309,201 +411,267 @@ k_grad_dmma(const double* __restrict__ Jg, const double* __restrict__ Dg,
         if (kt == 8 && t == 3) v = 0.0;
         a[m][kt] = v;
       }
-    }
-    // J is needed for the accumulator columns n = 2t, 2t+1 (elements of row-group
-    // 2t / 2t+1 of the C fragment), not for row g: C[row g][col] has row = element.
-    // Here M = element (row g), so J[x][r][el(g)] scales this thread's two values.
-#pragma unroll
-    for (int m = 0; m < kME; ++m) {
-      const int el = chunk_el(g, m);
 #pragma unroll
       for (int xr = 0; xr < 9; ++xr) Jr[m][xr] = sJ[xr * kCH + el];
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[slot]);     // everything is in registers now
+    if (wi.item + wi.stride < wi.nitems) grad_issue(s, bar, Jg, ug, wi.item + wi.stride, E, tma_ok, lane);
 
-    const long long e0 = (blockIdx.x + q * G) * kCH;
+    const long long e0 = wi.item * kCH;
+    if (lane == 0) tma_store_wait_read();          // previous blocks have left the stage
+    __syncwarp();
+
 #pragma unroll 1
-    for (int it = 0; it < DmmaShape::NT; ++it) {
+    for (int G = 0; G < L::NG; ++G) {
       double acc[kME][3][2];
 #pragma unroll
       for (int m = 0; m < kME; ++m)
 #pragma unroll
-        for (int r = 0; r < 3; ++r) { acc[m][r][0] = 0.0; acc[m][r][1] = 0.0; }
-      const double* bp = sB + (size_t)it * L::KT * 3 * 32 + lane;
+        for (int jt = 0; jt < 3; ++jt) { acc[m][jt][0] = 0.0; acc[m][jt][1] = 0.0; }
+      const double* bp = sB + (size_t)G * L::KT * 3 * 32 + lane;
 #pragma unroll
       for (int kt = 0; kt < L::KT; ++kt) {
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const double b = bp[(kt * 3 + r) * 32];
+        for (int jt = 0; jt < 3; ++jt) {
+          const double b = bp[(kt * 3 + jt) * 32];
 #pragma unroll
-          for (int m = 0; m < kME; ++m) dmma884(acc[m][r], a[m][kt], b);
+          for (int m = 0; m < kME; ++m) dmma884(acc[m][jt], a[m][kt], b);
         }
       }
-      const int i = 8 * it + 2 * t;
+      // lane holds T[dof 8G+2t+dl][r]: value v = 3*dl + r = 2*jt + h
+      const int i = 8 * G + 2 * t;
 #pragma unroll
       for (int m = 0; m < kME; ++m) {
-        const long long e = e0 + chunk_el(g, m);
-        if (e < E) {
+        const double T00 = acc[m][0][0], T01 = acc[m][0][1], T02 = acc[m][1][0];
+        const double T10 = acc[m][1][1], T11 = acc[m][2][0], T12 = acc[m][2][1];
 #pragma unroll
-          for (int x = 0; x < 3; ++x) {
-            const double o0 = fma(Jr[m][3 * x + 2], acc[m][2][0], fma(Jr[m][3 * x + 1], acc[m][1][0], Jr[m][3 * x] * acc[m][0][0]));
-            const double o1 = fma(Jr[m][3 * x + 2], acc[m][2][1], fma(Jr[m][3 * x + 1], acc[m][1][1], Jr[m][3 * x] * acc[m][0][1]));
-            double* o = outg + ((long long)x * E + e) * 35;
-            if (i < 35) stg_stream(o + i, o0);
-            if (i + 1 < 35) stg_stream(o + i + 1, o1);
-          }
+        for (int x = 0; x < 3; ++x) {
+          const double o0 = fma(Jr[m][3 * x + 2], T02, fma(Jr[m][3 * x + 1], T01, Jr[m][3 * x] * T00));
+          const double o1 = fma(Jr[m][3 * x + 2], T12, fma(Jr[m][3 * x + 1], T11, Jr[m][3 * x] * T10));
+          double* o = stage + x * OUT_BLOCK + chunk_el(g, m) * 35 + i;
+          o[0] = o0;
+          o[1] = o1;
         }
       }
     }
+    // ---- left-over dofs 32..34 x 3 r: DFMA partial sums over k = t (mod 4) ----
+    {
+      double accL[kME][9];
+#pragma unroll
+      for (int m = 0; m < kME; ++m)
+#pragma unroll
+        for (int c = 0; c < 9; ++c) accL[m][c] = 0.0;
+#pragma unroll
+      for (int kt = 0; kt < L::KT; ++kt) {
+        const double* lp = sL + (kt * 4 + t) * L::L_STRIDE;
+        double l[9];
+#pragma unroll
+        for (int c2 = 0; c2 < 4; ++c2) {
+          const double2 v = *reinterpret_cast<const double2*>(lp + 2 * c2);
+          l[2 * c2] = v.x; l[2 * c2 + 1] = v.y;
+        }
+        l[8] = lp[8];
+#pragma unroll
+        for (int m = 0; m < kME; ++m)
+#pragma unroll
+          for (int c = 0; c < 9; ++c) accL[m][c] = fma(a[m][kt], l[c], accL[m][c]);
+      }
+#pragma unroll
+      for (int m = 0; m < kME; ++m) {
+        double T[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) T[c] = quad_sum(accL[m][c]);
+        // lane t < 3 produces out[x = t][e][32..34]
+        const double j0 = t == 0 ? Jr[m][0] : (t == 1 ? Jr[m][3] : Jr[m][6]);
+        const double j1 = t == 0 ? Jr[m][1] : (t == 1 ? Jr[m][4] : Jr[m][7]);
+        const double j2 = t == 0 ? Jr[m][2] : (t == 1 ? Jr[m][5] : Jr[m][8]);
+        if (t < 3) {
+          double* o = stage + t * OUT_BLOCK + chunk_el(g, m) * 35 + 32;
+#pragma unroll
+          for (int d = 0; d < kNL; ++d)
+            o[d] = fma(j2, T[3 * d + 2], fma(j1, T[3 * d + 1], j0 * T[3 * d]));
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+#pragma unroll
+    for (int x = 0; x < 3; ++x)
+      flush_block(outg + ((long long)x * E + e0) * 35, stage + x * OUT_BLOCK, e0, E, tma_ok, lane);
+    if (lane == 0) tma_store_commit();
   }
+  if (lane == 0) tma_store_wait_all();
 }
 
 // ================================================================ LIFT =====
 // out_k[e,i] = sum_{f,j} Op(f,i,j) * Jf(e,f) * v_k[f,e,j];  K = (f,j) = 60 = 15 k-tiles
-// work item = (chunk, field): the ring streams one field of one chunk per slot
+// work item = (chunk, field): a slot holds one field of one chunk
 struct LiftLayout {
   static constexpr int KT = 15;
-  static constexpr int B_DOUBLES = KT * DmmaShape::NT * 32;           // 2400
+  static constexpr int B_MAIN = KT * kNT * 32;                        // 1920
+  static constexpr int B_LEFT = KT * 4 * 4;                           // 240
+  static constexpr int B_DOUBLES = B_MAIN + B_LEFT;
   static constexpr int V_SLAB = kCH * 15;                             // doubles per face
   static constexpr int SLOT_DOUBLES = 4 * V_SLAB + 4 * kCH;           // 1024 -> 8192 B
   static constexpr uint32_t SLOT_BYTES = SLOT_DOUBLES * 8;
 };
 
+template <bool FE>
+__device__ __forceinline__ void lift_issue(double* s, uint64_t* bar, const double* __restrict__ Jg,
+                                           const double* __restrict__ vg, long long chunk, long long E,
+                                           bool tma_ok, int lane) {
+  using L = LiftLayout;
+  const long long e0 = chunk * kCH;
+  if (tma_ok && e0 + kCH <= E) {
+    if (elect_one()) {
+      fence_proxy_async();
+      mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
+      for (int f = 0; f < 4; ++f)
+        tma_load_1d(s + f * L::V_SLAB, vg + ((long long)f * E + e0) * 15, L::V_SLAB * 8, bar);
+      if (FE) {
+        for (int f = 0; f < 4; ++f)   // Jface(f, e): 4 rows of kCH
+          tma_load_1d(s + 4 * L::V_SLAB + f * kCH, Jg + (long long)f * E + e0, kCH * 8, bar);
+      } else {                        // J(e, f): kCH*4 contiguous
+        tma_load_1d(s + 4 * L::V_SLAB, Jg + e0 * 4, 4 * kCH * 8, bar);
+      }
+    }
+  } else {
+    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+    for (int f = 0; f < 4; ++f)
+      for (int k = lane; k < L::V_SLAB; k += 32)
+        s[f * L::V_SLAB + k] = (k < ne * 15) ? vg[((long long)f * E + e0) * 15 + k] : 0.0;
+    for (int k = lane; k < 4 * kCH; k += 32) {
+      double v = 0.0;
+      if (FE) { const int f = k / kCH, el = k - f * kCH; if (el < ne) v = Jg[(long long)f * E + e0 + el]; }
+      else    { const int el = k / 4; if (el < ne) v = Jg[e0 * 4 + k]; }
+      s[4 * L::V_SLAB + k] = v;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+  }
+}
+
 template <int NW, bool FE>
-__global__ void __launch_bounds__((NW + 1) * 32, 1)
+__global__ void __launch_bounds__(NW * 32, 1)
 k_lift_dmma(const double* __restrict__ Jg, const double* __restrict__ Og, OpmatRows rows, int nrows,
-            long long E, int nslots, int tma_ok) {
+            long long E, int tma_ok, int stagger) {
   using L = LiftLayout;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sB = reinterpret_cast<double*>(smem_raw);
-  double* ring = sB + L::B_DOUBLES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)nslots * L::SLOT_DOUBLES);
-  uint64_t* empty = full + nslots;
+  double* sL = sB + L::B_MAIN;
+  double* slots = sB + L::B_DOUBLES;
+  double* stages = slots + (size_t)NW * L::SLOT_DOUBLES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * OUT_BLOCK);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // sB[(kt*NT + nt)*32 + lane] = Op(f, 8nt+g, j),  k = 4kt+t = 15 f + j
-  for (int idx = threadIdx.x; idx < L::B_DOUBLES; idx += blockDim.x) {
-    const int ln = idx & 31, nt = (idx >> 5) % DmmaShape::NT, kt = (idx >> 5) / DmmaShape::NT;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  // sB[(kt*4 + nt)*32 + lane] = Op(f, 8nt+g, j),  k = 4kt+t = 15 f + j
+  for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
+    const int ln = idx & 31, nt = (idx >> 5) % kNT, kt = (idx >> 5) / kNT;
     const int g = ln >> 2, t = ln & 3, k = 4 * kt + t, f = k / 15, j = k - 15 * f;
     const int i = 8 * nt + g;
+    sB[idx] = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
+  }
+  for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
+    const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
+    const int k = 4 * kt + t, f = k / 15, j = k - 15 * f, i = 32 + d;
     double v = 0.0;
-    if (i < 35) v = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
-    sB[idx] = v;
+    if (d < kNL) v = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
+    sL[idx] = v;
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nslots; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
     mbar_fence_init();
   }
   __syncthreads();
 
+  double* s = slots + (size_t)warp * L::SLOT_DOUBLES;
+  double* stage = stages + (size_t)warp * OUT_BLOCK;
+  uint64_t* bar = &bars[warp];
+  const double* sJ = s + 4 * L::V_SLAB;
   const long long nchunks = (E + kCH - 1) / kCH;
-  const long long nitems = nchunks * nrows;      // item = chunk * nrows + field
-  const long long G = gridDim.x;
-  // CTA b owns chunks b, b+G, ...; all fields of a chunk are consecutive items
-  const long long nqc = (nchunks > (long long)blockIdx.x) ? (nchunks - blockIdx.x + G - 1) / G : 0;
-  const long long nq = nqc * nrows;
-  (void)nitems;
-
-  if (warp == NW) {
-    for (long long q = 0; q < nq; ++q) {
-      const int slot = (int)(q % nslots);
-      const long long use = q / nslots;
-      if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
-      const long long qc = q / nrows;
-      const int fld = (int)(q - qc * nrows);
-      const long long e0 = (blockIdx.x + qc * G) * kCH;
-      const double* vg = static_cast<const double*>(rows.field[fld]);
-      double* s = ring + (size_t)slot * L::SLOT_DOUBLES;
-      const bool fast = tma_ok && e0 + kCH <= E;
-      if (fast) {
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&full[slot], L::SLOT_BYTES);
-          for (int f = 0; f < 4; ++f)
-            tma_load_1d(s + f * L::V_SLAB, vg + ((long long)f * E + e0) * 15, L::V_SLAB * 8, &full[slot]);
-          if (FE) {
-            for (int f = 0; f < 4; ++f)   // Jface(f, e): 4 rows of kCH
-              tma_load_1d(s + 4 * L::V_SLAB + f * kCH, Jg + (long long)f * E + e0, kCH * 8, &full[slot]);
-          } else {                        // J(e, f): kCH*4 contiguous
-            tma_load_1d(s + 4 * L::V_SLAB, Jg + e0 * 4, 4 * kCH * 8, &full[slot]);
-          }
-        }
-      } else {
-        const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-        for (int f = 0; f < 4; ++f)
-          for (int k = lane; k < L::V_SLAB; k += 32)
-            s[f * L::V_SLAB + k] = (k < ne * 15) ? vg[((long long)f * E + e0) * 15 + k] : 0.0;
-        for (int k = lane; k < 4 * kCH; k += 32) {
-          double v = 0.0;
-          if (FE) { const int f = k / kCH, el = k - f * kCH; if (el < ne) v = Jg[(long long)f * E + e0 + el]; }
-          else    { const int el = k / 4; if (el < ne) v = Jg[e0 * 4 + k]; }
-          s[4 * L::V_SLAB + k] = v;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[slot]);
-      }
-    }
-    return;
-  }
-
+  WorkIter wi = work_iter(NW, nchunks * nrows);      // item = chunk * nrows + field
   const int g = lane >> 2, t = lane & 3;
-  for (long long q = warp; q < nq; q += NW) {
-    const int slot = (int)(q % nslots);
-    const long long use = q / nslots;
-    mbar_wait(&full[slot], (uint32_t)(use & 1));
-    const double* s = ring + (size_t)slot * L::SLOT_DOUBLES;
-    const double* sJ = s + 4 * L::V_SLAB;
 
-    double acc[kME][DmmaShape::NT][2];
-    double Jf[kME][4];
+  if (wi.item < wi.nitems) {
+    const long long c = wi.item / nrows;
+    lift_issue<FE>(s, bar, Jg, static_cast<const double*>(rows.field[wi.item - c * nrows]), c, E, tma_ok, lane);
+  }
+  stagger_start(stagger, warp);
+  for (uint32_t n = 0; wi.item < wi.nitems; wi.item += wi.stride, ++n) {
+    mbar_wait(bar, n & 1u);
+    double a[kME][L::KT];
 #pragma unroll
     for (int m = 0; m < kME; ++m) {
       const int el = chunk_el(g, m);
 #pragma unroll
-      for (int f = 0; f < 4; ++f) Jf[m][f] = FE ? sJ[f * kCH + el] : sJ[el * 4 + f];
-#pragma unroll
-      for (int nt = 0; nt < DmmaShape::NT; ++nt) { acc[m][nt][0] = 0.0; acc[m][nt][1] = 0.0; }
-    }
-#pragma unroll
-    for (int kt = 0; kt < L::KT; ++kt) {
-      double a[kME];
-#pragma unroll
-      for (int m = 0; m < kME; ++m) {
-        const int el = chunk_el(g, m);
-        // k = 4kt + t = 15 f + j ; f and j are not compile-time (t is a lane id)
+      for (int kt = 0; kt < L::KT; ++kt) {
+        // k = 4kt + t = 15 f + j ; f and j depend on the lane (t)
         const int k = 4 * kt + t, f = k / 15, j = k - 15 * f;
-        const double jf = (f == 0) ? Jf[m][0] : (f == 1) ? Jf[m][1] : (f == 2) ? Jf[m][2] : Jf[m][3];
-        a[m] = jf * s[f * L::V_SLAB + el * 15 + j];
-      }
-      const double* bp = sB + (kt * DmmaShape::NT) * 32 + lane;
-#pragma unroll
-      for (int nt = 0; nt < DmmaShape::NT; ++nt) {
-        const double b = bp[nt * 32];
-#pragma unroll
-        for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m], b);
+        const double jf = FE ? sJ[f * kCH + el] : sJ[el * 4 + f];
+        a[m][kt] = jf * s[f * L::V_SLAB + el * 15 + j];
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[slot]);
-
-    const long long qc = q / nrows;
-    const int fld = (int)(q - qc * nrows);
-    const long long e0 = (blockIdx.x + qc * G) * kCH;
-    double* outg = static_cast<double*>(rows.out[fld]);
-#pragma unroll
-    for (int m = 0; m < kME; ++m) {
-      const long long e = e0 + chunk_el(g, m);
-      if (e < E) {
-        double* o = outg + e * 35;
-#pragma unroll
-        for (int nt = 0; nt < DmmaShape::NT; ++nt) {
-          const int i = 8 * nt + 2 * t;
-          if (i < 35) stg_stream(o + i, acc[m][nt][0]);
-          if (i + 1 < 35) stg_stream(o + i + 1, acc[m][nt][1]);
-        }
+    {
+      const long long nx = wi.item + wi.stride;
+      if (nx < wi.nitems) {
+        const long long c = nx / nrows;
+        lift_issue<FE>(s, bar, Jg, static_cast<const double*>(rows.field[nx - c * nrows]), c, E, tma_ok, lane);
       }
     }
+
+    double acc[kME][kNT][2];
+    double accL[2][kME][kNL];      // two partial sums per value: DFMA latency >> 6 chains
+#pragma unroll
+    for (int m = 0; m < kME; ++m) {
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt) { acc[m][nt][0] = 0.0; acc[m][nt][1] = 0.0; }
+#pragma unroll
+      for (int d = 0; d < kNL; ++d) { accL[0][m][d] = 0.0; accL[1][m][d] = 0.0; }
+    }
+#pragma unroll
+    for (int kt = 0; kt < L::KT; ++kt) {
+      const double* bp = sB + (kt * kNT) * 32 + lane;
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt) {
+        const double b = bp[nt * 32];
+#pragma unroll
+        for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m][kt], b);
+      }
+      const double2 l01 = *reinterpret_cast<const double2*>(sL + (kt * 4 + t) * 4);
+      const double l2 = sL[(kt * 4 + t) * 4 + 2];
+#pragma unroll
+      for (int m = 0; m < kME; ++m) {
+        accL[kt & 1][m][0] = fma(a[m][kt], l01.x, accL[kt & 1][m][0]);
+        accL[kt & 1][m][1] = fma(a[m][kt], l01.y, accL[kt & 1][m][1]);
+        accL[kt & 1][m][2] = fma(a[m][kt], l2, accL[kt & 1][m][2]);
+      }
+    }
+
+    const long long c = wi.item / nrows;
+    const int fld = (int)(wi.item - c * nrows);
+    const long long e0 = c * kCH;
+    double* outg = static_cast<double*>(rows.out[fld]);
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < kME; ++m) {
+      double* o = stage + chunk_el(g, m) * 35;
+      const double l0 = quad_sum(accL[0][m][0] + accL[1][m][0]), l1 = quad_sum(accL[0][m][1] + accL[1][m][1]),
+                   l2 = quad_sum(accL[0][m][2] + accL[1][m][2]);
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt) {
+        o[8 * nt + 2 * t] = acc[m][nt][0];
+        o[8 * nt + 2 * t + 1] = acc[m][nt][1];
+      }
+      if (t < kNL) o[32 + t] = t == 0 ? l0 : (t == 1 ? l1 : l2);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    flush_block(outg + e0 * 35, stage, e0, E, tma_ok, lane);
+    if (lane == 0) tma_store_commit();
   }
+  if (lane == 0) tma_store_wait_all();
 }
 
 // ------------------------------------------------------------ launchers ----
@@ -520,59 +688,73 @@ static int set_smem(K kernel, size_t smem) {
   return e == cudaSuccess ? FNSM_OK : (int)e;
 }
 
-static int launch_dmma(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows,
-                       int n_outer, int ni, int nj, long long E, const fnsm_cfg* cfg,
-                       const DevInfo& di, cudaStream_t st) {
-  (void)n_outer; (void)ni; (void)nj;
-  constexpr int NW = 8;
-  if (cfg && cfg->threads != 0 && cfg->threads != (NW + 1) * 32) return FNSM_E_BAD_CONFIG;
-  int extra = (cfg && cfg->stages > 0) ? cfg->stages : 4;
-  if (extra < 1 || extra > 24) return FNSM_E_BAD_CONFIG;
-  int nslots = NW + extra;
+template <int NW>
+static int launch_dmma_nw(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows,
+                          long long E, const fnsm_cfg* cfg, const DevInfo& di, cudaStream_t st) {
   const long long nchunks = (E + kCH - 1) / kCH;
-  long long grid = di.sms;   // one persistent CTA per SM (launch bound 1 CTA/SM)
-  if (cfg && cfg->ctas_per_sm > 1) return FNSM_E_BAD_CONFIG;
-  if (grid > nchunks) grid = nchunks;
   const double* J = static_cast<const double*>(jac);
   const double* O = static_cast<const double*>(op);
-  const int threads = (NW + 1) * 32;
+  constexpr int threads = NW * 32;
   int tma_ok = (E % 2 == 0) && aligned16(jac);
-  for (int r = 0; r < nrows; ++r) tma_ok = tma_ok && aligned16(rows.field[r]);
+  for (int r = 0; r < nrows; ++r) tma_ok = tma_ok && aligned16(rows.field[r]) && aligned16(rows.out[r]);
+  if (cfg && (cfg->reserved[0] & 1)) tma_ok = 0;    // debug flag: force the plain-load path
+  if (cfg && kind == FNSM_OP_DIV) tma_ok |= cfg->reserved[0] & 6;   // profiling aids: skip loads / stores
+  const int stagger = cfg ? cfg->reserved[1] : 0;   // start-up de-synchronisation, cycles per warp
+  if (stagger < 0 || stagger > (1 << 20)) return FNSM_E_BAD_CONFIG;
+  auto grid_for_items = [&](long long nitems) {
+    long long grid = di.sms;                          // one persistent CTA per SM
+    const long long need = (nitems + NW - 1) / NW;
+    return (unsigned)(grid < need ? grid : need);
+  };
 
   if (kind == FNSM_OP_DIV || kind == FNSM_OP_GRAD) {
     const bool is_div = kind == FNSM_OP_DIV;
     const size_t slot_d = is_div ? DivLayout::SLOT_DOUBLES : GradLayout::SLOT_DOUBLES;
     const size_t b_d = is_div ? DivLayout::B_DOUBLES : GradLayout::B_DOUBLES;
-    size_t smem = 8 * (b_d + (size_t)nslots * slot_d) + 16 * (size_t)nslots;
-    while (smem > (size_t)di.max_smem_optin && nslots > NW + 1) {
-      --nslots;
-      smem = 8 * (b_d + (size_t)nslots * slot_d) + 16 * (size_t)nslots;
-    }
+    const size_t stage_d = is_div ? OUT_BLOCK : 3 * OUT_BLOCK;
+    const size_t smem = 8 * (b_d + (size_t)NW * (slot_d + stage_d)) + 8 * (size_t)NW;
     if (smem > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
     for (int r = 0; r < nrows; ++r) {
       const double* u = static_cast<const double*>(rows.field[r]);
       double* out = static_cast<double*>(rows.out[r]);
       if (is_div) {
         if (int rc = set_smem(k_div_dmma<NW>, smem)) return rc;
-        k_div_dmma<NW><<<(unsigned)grid, threads, smem, st>>>(J, O, u, out, E, nslots, tma_ok);
+        k_div_dmma<NW><<<grid_for_items(nchunks), threads, smem, st>>>(J, O, u, out, E, tma_ok, stagger);
       } else {
         if (int rc = set_smem(k_grad_dmma<NW>, smem)) return rc;
-        k_grad_dmma<NW><<<(unsigned)grid, threads, smem, st>>>(J, O, u, out, E, nslots, tma_ok);
+        k_grad_dmma<NW><<<grid_for_items(nchunks), threads, smem, st>>>(J, O, u, out, E, tma_ok, stagger);
       }
       if (int rc = post_launch()) return rc;
     }
     return FNSM_OK;
   }
-  size_t smem = 8 * ((size_t)LiftLayout::B_DOUBLES + (size_t)nslots * LiftLayout::SLOT_DOUBLES) + 16 * (size_t)nslots;
+  const size_t smem = 8 * ((size_t)LiftLayout::B_DOUBLES + (size_t)NW * (LiftLayout::SLOT_DOUBLES + OUT_BLOCK)) + 8 * (size_t)NW;
   if (smem > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
+  const unsigned grid = grid_for_items(nchunks * nrows);
   if (kind == FNSM_OP_LIFT_FE) {
     if (int rc = set_smem(k_lift_dmma<NW, true>, smem)) return rc;
-    k_lift_dmma<NW, true><<<(unsigned)grid, threads, smem, st>>>(J, O, rows, nrows, E, nslots, tma_ok);
+    k_lift_dmma<NW, true><<<grid, threads, smem, st>>>(J, O, rows, nrows, E, tma_ok, stagger);
   } else {
     if (int rc = set_smem(k_lift_dmma<NW, false>, smem)) return rc;
-    k_lift_dmma<NW, false><<<(unsigned)grid, threads, smem, st>>>(J, O, rows, nrows, E, nslots, tma_ok);
+    k_lift_dmma<NW, false><<<grid, threads, smem, st>>>(J, O, rows, nrows, E, tma_ok, stagger);
   }
   return post_launch();
+}
+
+static int launch_dmma(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows,
+                       int n_outer, int ni, int nj, long long E, const fnsm_cfg* cfg,
+                       const DevInfo& di, cudaStream_t st) {
+  (void)n_outer; (void)ni; (void)nj;
+  if (cfg && cfg->ctas_per_sm > 1) return FNSM_E_BAD_CONFIG;
+  if (cfg && (cfg->stages < 0 || cfg->stages > 1)) return FNSM_E_BAD_CONFIG;
+  const int threads = (cfg && cfg->threads != 0) ? cfg->threads : 256;
+  switch (threads) {
+    case 128: return launch_dmma_nw<4>(kind, jac, op, rows, nrows, E, cfg, di, st);
+    case 256: return launch_dmma_nw<8>(kind, jac, op, rows, nrows, E, cfg, di, st);
+    case 320: return launch_dmma_nw<10>(kind, jac, op, rows, nrows, E, cfg, di, st);
+    case 384: return launch_dmma_nw<12>(kind, jac, op, rows, nrows, E, cfg, di, st);
+    default: return FNSM_E_BAD_CONFIG;
+  }
 }
 
 // wave_3d_p4: placeholder sequencing of the three dmma kernels until the

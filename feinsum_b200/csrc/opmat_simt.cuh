@@ -1,4 +1,4 @@
-// Variant 0 ("simt") of the operator-matrix x element-batch kernels: run-time
+// Variant 2 ("simt") of the operator-matrix x element-batch kernels: run-time
 // sized, any ndim / ndof, fp64 and fp32, plain loads.  It follows the thread
 // layout of the reference's first-generation transforms (thread <-> (element,
 // output dof), operator matrix resident in local memory, J-scaling hoisted out

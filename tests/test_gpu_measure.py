@@ -34,7 +34,7 @@ def test_pprint_roofline_comparison(cq):
     # reference test/test_measure.py:55-81, with a launch-parameter transform
     s = measure.stringify_comparison_vs_roofline(
         E.grad(), cq=cq,
-        transform=lambda t_unit, insn_match, kernel_name: t_unit.with_params(variant=0, tile_e=32),
+        transform=lambda t_unit, insn_match, kernel_name: t_unit.with_params(variant=2, tile_e=32),
         long_dim_length=500,
     )
     assert "Measured GOps/s" in s and "float64" in s
