@@ -143,9 +143,6 @@ def make_cfg(params: dict[str, Any] | None) -> Any:
         if key == "flags":  # debug bits (bit 0: force the plain-load path of the dmma kernels)
             cfg.reserved[0] = int(val)
             continue
-        if key == "stagger":  # dmma kernels: start-up de-synchronisation, cycles per warp
-            cfg.reserved[1] = int(val)
-            continue
         if key not in known:
             raise InvalidParameterError(f"unknown launch parameter '{key}'")
         setattr(cfg, key, int(val))

@@ -14,9 +14,14 @@
 //     accumulators afterwards -- the hoisting the reference's transforms do,
 //     tuning/impls/xre_rij_ej_to_xei.py:104-117, xre_rij_xej_to_ei_v6.py:212-248,
 //     ifj_fe_fej_to_ei_v3.py:94-105), and immediately re-arms the slot with the
-//     1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of its NEXT
+//     TMA tensor copies (cp.async.bulk.tensor + mbarrier complete_tx) of its NEXT
 //     work item, which then land while the warp issues its DMMAs.  Since only
 //     the owning warp ever waits on a slot's barrier, phases cannot alias.
+//   * TMA descriptors (tensor maps) view the element axis in PAIRS of elements
+//     (70 / 30 doubles = 560 / 240 B rows, a multiple of 16 B), so one chunk is
+//     ONE box per operand: 2 loads + 1 store per work item instead of 10 + 3
+//     1-D copies -- the per-SM TMA unit was op-count bound with those -- and the
+//     hardware zero-fills / clips the tail chunk.
 //   * B fragments (the operator, zero padded in K to multiples of 4) sit in
 //     shared memory in fragment order [tile][lane] -> conflict-free LDS.64,
 //     each shared by the ME = 2 element tiles of a 16-element chunk.
@@ -29,6 +34,7 @@
 //
 // Unaligned inputs (odd E, misaligned base, tail chunk) take a plain-load path.
 #pragma once
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through cudart)
 #include "common.cuh"
 #include "opmat_simt.cuh"
 
@@ -66,16 +72,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// 1-D bulk copy global -> shared, completion signalled on an mbarrier (TMA unit)
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+// TMA tensor copies global -> shared (completion on an mbarrier) and shared -> global
+// (bulk async-group of the issuing thread).  `tm` points at a __grid_constant__ CUtensorMap.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      :: "r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
-// 1-D bulk copy shared -> global (TMA unit), tracked by the bulk async-group of the issuing thread
-__device__ __forceinline__ void tma_store_1d(void* dst, const void* src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-               :: "l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      :: "r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               :: "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+               :: "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src)) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all earlier bulk stores of this thread have finished READING shared memory
@@ -110,28 +125,22 @@ __device__ __forceinline__ int chunk_el(int g, int m) { return 4 * (g & 3) + (g 
 
 constexpr int OUT_BLOCK = kCH * 35;   // doubles of one [16 elements][35 dofs] output block
 
-// Flush one staged [kCH][35] block to out[e0 .. e0+kCH) (row length 35, contiguous):
-// one TMA bulk store when aligned and complete, coalesced plain stores otherwise.
-// Call with the whole warp after __syncwarp() made the staged values visible.
-__device__ __forceinline__ void flush_block(double* __restrict__ dst, const double* stage, long long e0,
-                                            long long E, bool tma_ok, int lane) {
-  if (tma_ok && e0 + kCH <= E) {
-    if (elect_one()) tma_store_1d(dst, stage, OUT_BLOCK * 8);
-  } else {
-    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-    for (int k = lane; k < ne * 35; k += 32) dst[k] = stage[k];
-  }
+// plain-path flush of one staged [kCH][35] block to out[e0 .. e0+kCH): coalesced stores
+__device__ __forceinline__ void flush_plain(double* __restrict__ dst, const double* stage, long long e0,
+                                            long long E, int lane) {
+  const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+  for (int k = lane; k < ne * 35; k += 32) dst[k] = stage[k];
 }
 
-// De-synchronise the warps of a CTA once at start-up (warp w waits w * cycles):
-// all warps run the same phases (slot -> registers, DMMA stream, stage + store);
-// in lock-step the non-DMMA phases of every warp coincide and the FP64 pipe idles.
-__device__ __forceinline__ void stagger_start(int cycles, int warp) {
-  if (cycles > 0) {
-    const long long t0 = clock64(), wait = (long long)cycles * warp;
-    while (clock64() - t0 < wait) {}
-  }
-}
+// tensor maps of one grad / div launch (element axis in pairs, see file header)
+struct OpMaps { CUtensorMap in, jac, out; };
+// lift: one Jacobian map, one input and one output map per field
+struct LiftMaps { CUtensorMap jac; CUtensorMap in[8]; CUtensorMap out[8]; };
+
+// launch flags (low bits of the kernels' `flags` argument)
+constexpr int kFlagTma = 1;        // operands qualify for the TMA path
+constexpr int kFlagNoLoad = 2;     // profiling aid: skip loads  (results invalid)
+constexpr int kFlagNoStore = 4;    // profiling aid: skip stores (results invalid)
 
 struct WorkIter {
   long long item, stride, nitems;
@@ -157,19 +166,17 @@ struct DivLayout {
   static constexpr uint32_t SLOT_BYTES = SLOT_DOUBLES * 8;
 };
 
-__device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const double* __restrict__ Jg,
-                                          const double* __restrict__ ug, long long chunk, long long E,
-                                          bool tma_ok, int lane) {
+__device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps* maps,
+                                          const double* __restrict__ Jg, const double* __restrict__ ug,
+                                          long long chunk, long long E, bool tma, int lane) {
   using L = DivLayout;
   const long long e0 = chunk * kCH;
-  if (tma_ok && e0 + kCH <= E) {
+  if (tma) {
     if (elect_one()) {
       fence_proxy_async();
       mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
-      for (int x = 0; x < 3; ++x)
-        tma_load_1d(s + x * L::U_SLAB, ug + ((long long)x * E + e0) * 35, L::U_SLAB * 8, bar);
-      for (int xr = 0; xr < 9; ++xr)
-        tma_load_1d(s + 3 * L::U_SLAB + xr * kCH, Jg + (long long)xr * E + e0, kCH * 8, bar);
+      tma_load_3d(s, &maps->in, 0, (int)(chunk * (kCH / 2)), 0, bar);          // u[0..2][16 el][35]
+      tma_load_2d(s + 3 * L::U_SLAB, &maps->jac, (int)e0, 0, bar);              // J[9][16 el]
     }
   } else {
     const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
@@ -187,9 +194,8 @@ __device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const double
 
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
-k_div_dmma(const double* __restrict__ Jg, const double* __restrict__ Dg,
-           const double* __restrict__ ug, double* __restrict__ outg,
-           long long E, int tma_ok, int stagger) {
+k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, const double* __restrict__ Dg,
+           const double* __restrict__ ug, double* __restrict__ outg, long long E, int flags) {
   using L = DivLayout;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sB = reinterpret_cast<double*>(smem_raw);
@@ -226,10 +232,8 @@ k_div_dmma(const double* __restrict__ Jg, const double* __restrict__ Dg,
   WorkIter wi = work_iter(NW, nchunks);
   const int g = lane >> 2, t = lane & 3;
 
-  const bool dbg_noload = tma_ok & 2, dbg_nostore = tma_ok & 4;   // profiling aids (results invalid)
-  tma_ok &= 1;
-  if (wi.item < wi.nitems && !dbg_noload) div_issue(s, bar, Jg, ug, wi.item, E, tma_ok, lane);
-  stagger_start(stagger, warp);
+  const bool tma = flags & kFlagTma, dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
+  if (wi.item < wi.nitems && !dbg_noload) div_issue(s, bar, &maps, Jg, ug, wi.item, E, tma, lane);
   for (uint32_t n = 0; wi.item < wi.nitems; wi.item += wi.stride, ++n) {
     if (!dbg_noload) mbar_wait(bar, n & 1u);
     // ---- slot -> A fragments (Jacobian folded in) ----
@@ -255,7 +259,8 @@ k_div_dmma(const double* __restrict__ Jg, const double* __restrict__ Dg,
       }
     }
     __syncwarp();                                  // every lane is done reading the slot
-    if (wi.item + wi.stride < wi.nitems && !dbg_noload) div_issue(s, bar, Jg, ug, wi.item + wi.stride, E, tma_ok, lane);
+    if (wi.item + wi.stride < wi.nitems && !dbg_noload)
+      div_issue(s, bar, &maps, Jg, ug, wi.item + wi.stride, E, tma, lane);
 
     // ---- DMMA stream ----
     double acc[kME][kNT][2];
@@ -304,8 +309,11 @@ k_div_dmma(const double* __restrict__ Jg, const double* __restrict__ Dg,
     fence_proxy_async();
     __syncwarp();
     if (!dbg_nostore) {
-      flush_block(outg + e0 * 35, stage, e0, E, tma_ok, lane);
-      if (lane == 0) tma_store_commit();
+      if (tma) {
+        if (lane == 0) { tma_store_2d(&maps.out, stage, 0, (int)(wi.item * (kCH / 2))); tma_store_commit(); }
+      } else {
+        flush_plain(outg + e0 * 35, stage, e0, E, lane);
+      }
     }
   }
   if (lane == 0) tma_store_wait_all();
@@ -313,34 +321,31 @@ k_div_dmma(const double* __restrict__ Jg, const double* __restrict__ Dg,
 
 // ================================================================ GRAD =====
 // T[r][e][i] = sum_j D[r,i,j] u[e,j];  out[x,e,i] = sum_r J[x,r,e] T[r][e][i]
-// k-tiles kt <-> j = 4*kt + t (9 tiles).  Column tiles: group G (8 dofs) x 3
-// tiles; tile jt, column c <-> value v = 2*jt + (c&1) of lane t = c>>1, which is
-// (dof 8G + 2t + v/3, r = v%3): a lane ends up with all three r of its two dofs,
-// so J is applied in registers.
+// k-tiles kt <-> j = 4*kt + t (9 tiles).  N = (dof, r) = 105 columns in 14 column
+// tiles laid out so that a lane ends up with whole r-triples: lane t owns dofs
+// 9t .. 9t+8 (t = 3: 27..34 plus one pad); its value v = 2*tile + h (h = column
+// parity inside the tile, column c = 2t + h) is (dof 9t + v/3, r = v%3).  J is then
+// applied in registers -- no shuffles, no left-over pass; 105/112 of the columns are useful.
 struct GradLayout {
   static constexpr int KT = 9;
-  static constexpr int NG = 4;
-  static constexpr int B_MAIN = NG * KT * 3 * 32;                     // 3456
-  static constexpr int L_STRIDE = 10;                                 // 9 columns (dof-major, r minor) + pad
-  static constexpr int B_LEFT = KT * 4 * L_STRIDE;                    // 360
-  static constexpr int B_DOUBLES = B_MAIN + B_LEFT;
+  static constexpr int NTILE = 14;
+  static constexpr int B_DOUBLES = NTILE * KT * 32;                   // 4032
   static constexpr int U_SLAB = kCH * 35;
   static constexpr int SLOT_DOUBLES = U_SLAB + 9 * kCH;               // 704 -> 5632 B
   static constexpr uint32_t SLOT_BYTES = SLOT_DOUBLES * 8;
 };
 
-__device__ __forceinline__ void grad_issue(double* s, uint64_t* bar, const double* __restrict__ Jg,
-                                           const double* __restrict__ ug, long long chunk, long long E,
-                                           bool tma_ok, int lane) {
+__device__ __forceinline__ void grad_issue(double* s, uint64_t* bar, const OpMaps* maps,
+                                           const double* __restrict__ Jg, const double* __restrict__ ug,
+                                           long long chunk, long long E, bool tma, int lane) {
   using L = GradLayout;
   const long long e0 = chunk * kCH;
-  if (tma_ok && e0 + kCH <= E) {
+  if (tma) {
     if (elect_one()) {
       fence_proxy_async();
       mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
-      tma_load_1d(s, ug + e0 * 35, L::U_SLAB * 8, bar);
-      for (int xr = 0; xr < 9; ++xr)
-        tma_load_1d(s + L::U_SLAB + xr * kCH, Jg + (long long)xr * E + e0, kCH * 8, bar);
+      tma_load_2d(s, &maps->in, 0, (int)(chunk * (kCH / 2)), bar);               // u[16 el][35]
+      tma_load_2d(s + L::U_SLAB, &maps->jac, (int)e0, 0, bar);                   // J[9][16 el]
     }
   } else {
     const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
@@ -354,33 +359,68 @@ __device__ __forceinline__ void grad_issue(double* s, uint64_t* bar, const doubl
   }
 }
 
+// one group of NTG column tiles (starting at tile T0): DMMAs, then J applied to the
+// NTG*2/3 complete (dof, r)-triples this lane now holds, results staged in shared memory
+template <int T0, int NTG>
+__device__ __forceinline__ void grad_group(const double* __restrict__ sB, const double (&a)[kME][GradLayout::KT],
+                                           const double (&Jr)[kME][9], double* stage, int g, int t, int lane) {
+  using L = GradLayout;
+  double acc[kME][NTG][2];
+#pragma unroll
+  for (int m = 0; m < kME; ++m)
+#pragma unroll
+    for (int jt = 0; jt < NTG; ++jt) { acc[m][jt][0] = 0.0; acc[m][jt][1] = 0.0; }
+#pragma unroll
+  for (int kt = 0; kt < L::KT; ++kt) {
+#pragma unroll
+    for (int jt = 0; jt < NTG; ++jt) {
+      const double b = sB[((T0 + jt) * L::KT + kt) * 32 + lane];
+#pragma unroll
+      for (int m = 0; m < kME; ++m) dmma884(acc[m][jt], a[m][kt], b);
+    }
+  }
+  if (T0 == 0) {                             // first write of this chunk into the stage:
+    if (lane == 0) tma_store_wait_read();    // the previous chunk's bulk store must have read it out
+    __syncwarp();
+  }
+  constexpr int V0 = 2 * T0;                 // first value index of this group (multiple of 3 by construction)
+  static_assert(V0 % 3 == 0, "groups must start on a triple boundary");
+  constexpr int NTRI = (2 * NTG) / 3;        // complete triples in the group
+#pragma unroll
+  for (int m = 0; m < kME; ++m) {
+    double* o = stage + chunk_el(g, m) * 35 + 9 * t + V0 / 3;
+#pragma unroll
+    for (int q = 0; q < NTRI; ++q) {
+      const double T0v = acc[m][(3 * q) >> 1][(3 * q) & 1];
+      const double T1v = acc[m][(3 * q + 1) >> 1][(3 * q + 1) & 1];
+      const double T2v = acc[m][(3 * q + 2) >> 1][(3 * q + 2) & 1];
+      if (V0 / 3 + q < 8 || t < 3) {          // dof 9t + 8 exists only for t < 3
+#pragma unroll
+        for (int x = 0; x < 3; ++x)
+          o[x * OUT_BLOCK + q] = fma(Jr[m][3 * x + 2], T2v, fma(Jr[m][3 * x + 1], T1v, Jr[m][3 * x] * T0v));
+      }
+    }
+  }
+}
+
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
-k_grad_dmma(const double* __restrict__ Jg, const double* __restrict__ Dg,
-            const double* __restrict__ ug, double* __restrict__ outg,
-            long long E, int tma_ok, int stagger) {
+k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, const double* __restrict__ Dg,
+            const double* __restrict__ ug, double* __restrict__ outg, long long E, int flags) {
   using L = GradLayout;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sB = reinterpret_cast<double*>(smem_raw);
-  double* sL = sB + L::B_MAIN;
   double* slots = sB + L::B_DOUBLES;
   double* stages = slots + (size_t)NW * L::SLOT_DOUBLES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * 3 * OUT_BLOCK);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  // sB[((G*KT + kt)*3 + jt)*32 + lane]: column c = g of tile jt
-  for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
-    const int ln = idx & 31, jt = (idx >> 5) % 3, kt = ((idx >> 5) / 3) % L::KT, G = (idx >> 5) / (3 * L::KT);
+  // sB[(tile*KT + kt)*32 + lane]: B[k = t][n = c], c = lane>>2 -> value v = 2*tile + (c&1) of lane c>>1
+  for (int idx = threadIdx.x; idx < L::B_DOUBLES; idx += blockDim.x) {
+    const int ln = idx & 31, kt = (idx >> 5) % L::KT, tile = (idx >> 5) / L::KT;
     const int c = ln >> 2, t = ln & 3;
-    const int v = 2 * jt + (c & 1);
-    const int i = 8 * G + 2 * (c >> 1) + v / 3, r = v % 3, j = 4 * kt + t;
-    sB[idx] = (j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
-  }
-  // sL[(kt*4 + t)*10 + 3*d + r] = D[r][32+d][4kt+t]
-  for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
-    const int col = idx % L::L_STRIDE, t = (idx / L::L_STRIDE) & 3, kt = idx / (4 * L::L_STRIDE);
-    const int d = col / 3, r = col - 3 * d, j = 4 * kt + t;
-    sL[idx] = (col < 9 && j < 35) ? Dg[(r * 35 + 32 + d) * 35 + j] : 0.0;
+    const int v = 2 * tile + (c & 1), i = 9 * (c >> 1) + v / 3, r = v % 3, j = 4 * kt + t;
+    sB[idx] = (v < 27 && i < 35 && j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
   }
   if (threadIdx.x == 0) {
     for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
@@ -396,10 +436,10 @@ k_grad_dmma(const double* __restrict__ Jg, const double* __restrict__ Dg,
   WorkIter wi = work_iter(NW, nchunks);
   const int g = lane >> 2, t = lane & 3;
 
-  if (wi.item < wi.nitems) grad_issue(s, bar, Jg, ug, wi.item, E, tma_ok, lane);
-  stagger_start(stagger, warp);
+  const bool tma = flags & kFlagTma, dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
+  if (wi.item < wi.nitems && !dbg_noload) grad_issue(s, bar, &maps, Jg, ug, wi.item, E, tma, lane);
   for (uint32_t n = 0; wi.item < wi.nitems; wi.item += wi.stride, ++n) {
-    mbar_wait(bar, n & 1u);
+    if (!dbg_noload) mbar_wait(bar, n & 1u);
     double a[kME][L::KT];
     double Jr[kME][9];
 #pragma unroll
@@ -415,90 +455,26 @@ k_grad_dmma(const double* __restrict__ Jg, const double* __restrict__ Dg,
       for (int xr = 0; xr < 9; ++xr) Jr[m][xr] = sJ[xr * kCH + el];
     }
     __syncwarp();
-    if (wi.item + wi.stride < wi.nitems) grad_issue(s, bar, Jg, ug, wi.item + wi.stride, E, tma_ok, lane);
+    if (wi.item + wi.stride < wi.nitems && !dbg_noload)
+      grad_issue(s, bar, &maps, Jg, ug, wi.item + wi.stride, E, tma, lane);
 
     const long long e0 = wi.item * kCH;
-    if (lane == 0) tma_store_wait_read();          // previous blocks have left the stage
-    __syncwarp();
-
-#pragma unroll 1
-    for (int G = 0; G < L::NG; ++G) {
-      double acc[kME][3][2];
-#pragma unroll
-      for (int m = 0; m < kME; ++m)
-#pragma unroll
-        for (int jt = 0; jt < 3; ++jt) { acc[m][jt][0] = 0.0; acc[m][jt][1] = 0.0; }
-      const double* bp = sB + (size_t)G * L::KT * 3 * 32 + lane;
-#pragma unroll
-      for (int kt = 0; kt < L::KT; ++kt) {
-#pragma unroll
-        for (int jt = 0; jt < 3; ++jt) {
-          const double b = bp[(kt * 3 + jt) * 32];
-#pragma unroll
-          for (int m = 0; m < kME; ++m) dmma884(acc[m][jt], a[m][kt], b);
-        }
-      }
-      // lane holds T[dof 8G+2t+dl][r]: value v = 3*dl + r = 2*jt + h
-      const int i = 8 * G + 2 * t;
-#pragma unroll
-      for (int m = 0; m < kME; ++m) {
-        const double T00 = acc[m][0][0], T01 = acc[m][0][1], T02 = acc[m][1][0];
-        const double T10 = acc[m][1][1], T11 = acc[m][2][0], T12 = acc[m][2][1];
-#pragma unroll
-        for (int x = 0; x < 3; ++x) {
-          const double o0 = fma(Jr[m][3 * x + 2], T02, fma(Jr[m][3 * x + 1], T01, Jr[m][3 * x] * T00));
-          const double o1 = fma(Jr[m][3 * x + 2], T12, fma(Jr[m][3 * x + 1], T11, Jr[m][3 * x] * T10));
-          double* o = stage + x * OUT_BLOCK + chunk_el(g, m) * 35 + i;
-          o[0] = o0;
-          o[1] = o1;
-        }
-      }
-    }
-    // ---- left-over dofs 32..34 x 3 r: DFMA partial sums over k = t (mod 4) ----
-    {
-      double accL[kME][9];
-#pragma unroll
-      for (int m = 0; m < kME; ++m)
-#pragma unroll
-        for (int c = 0; c < 9; ++c) accL[m][c] = 0.0;
-#pragma unroll
-      for (int kt = 0; kt < L::KT; ++kt) {
-        const double* lp = sL + (kt * 4 + t) * L::L_STRIDE;
-        double l[9];
-#pragma unroll
-        for (int c2 = 0; c2 < 4; ++c2) {
-          const double2 v = *reinterpret_cast<const double2*>(lp + 2 * c2);
-          l[2 * c2] = v.x; l[2 * c2 + 1] = v.y;
-        }
-        l[8] = lp[8];
-#pragma unroll
-        for (int m = 0; m < kME; ++m)
-#pragma unroll
-          for (int c = 0; c < 9; ++c) accL[m][c] = fma(a[m][kt], l[c], accL[m][c]);
-      }
-#pragma unroll
-      for (int m = 0; m < kME; ++m) {
-        double T[9];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) T[c] = quad_sum(accL[m][c]);
-        // lane t < 3 produces out[x = t][e][32..34]
-        const double j0 = t == 0 ? Jr[m][0] : (t == 1 ? Jr[m][3] : Jr[m][6]);
-        const double j1 = t == 0 ? Jr[m][1] : (t == 1 ? Jr[m][4] : Jr[m][7]);
-        const double j2 = t == 0 ? Jr[m][2] : (t == 1 ? Jr[m][5] : Jr[m][8]);
-        if (t < 3) {
-          double* o = stage + t * OUT_BLOCK + chunk_el(g, m) * 35 + 32;
-#pragma unroll
-          for (int d = 0; d < kNL; ++d)
-            o[d] = fma(j2, T[3 * d + 2], fma(j1, T[3 * d + 1], j0 * T[3 * d]));
-        }
-      }
-    }
+    grad_group<0, 3>(sB, a, Jr, stage, g, t, lane);
+    grad_group<3, 3>(sB, a, Jr, stage, g, t, lane);
+    grad_group<6, 3>(sB, a, Jr, stage, g, t, lane);
+    grad_group<9, 3>(sB, a, Jr, stage, g, t, lane);
+    grad_group<12, 2>(sB, a, Jr, stage, g, t, lane);
     fence_proxy_async();
     __syncwarp();
+    if (!dbg_nostore) {
+      if (tma) {
+        if (lane == 0) { tma_store_3d(&maps.out, stage, 0, (int)(wi.item * (kCH / 2)), 0); tma_store_commit(); }
+      } else {
 #pragma unroll
-    for (int x = 0; x < 3; ++x)
-      flush_block(outg + ((long long)x * E + e0) * 35, stage + x * OUT_BLOCK, e0, E, tma_ok, lane);
-    if (lane == 0) tma_store_commit();
+        for (int x = 0; x < 3; ++x)
+          flush_plain(outg + ((long long)x * E + e0) * 35, stage + x * OUT_BLOCK, e0, E, lane);
+      }
+    }
   }
   if (lane == 0) tma_store_wait_all();
 }
@@ -517,23 +493,19 @@ struct LiftLayout {
 };
 
 template <bool FE>
-__device__ __forceinline__ void lift_issue(double* s, uint64_t* bar, const double* __restrict__ Jg,
+__device__ __forceinline__ void lift_issue(double* s, uint64_t* bar, const CUtensorMap* map_v,
+                                           const CUtensorMap* map_j, const double* __restrict__ Jg,
                                            const double* __restrict__ vg, long long chunk, long long E,
-                                           bool tma_ok, int lane) {
+                                           bool tma, int lane) {
   using L = LiftLayout;
   const long long e0 = chunk * kCH;
-  if (tma_ok && e0 + kCH <= E) {
+  if (tma) {
     if (elect_one()) {
       fence_proxy_async();
       mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
-      for (int f = 0; f < 4; ++f)
-        tma_load_1d(s + f * L::V_SLAB, vg + ((long long)f * E + e0) * 15, L::V_SLAB * 8, bar);
-      if (FE) {
-        for (int f = 0; f < 4; ++f)   // Jface(f, e): 4 rows of kCH
-          tma_load_1d(s + 4 * L::V_SLAB + f * kCH, Jg + (long long)f * E + e0, kCH * 8, bar);
-      } else {                        // J(e, f): kCH*4 contiguous
-        tma_load_1d(s + 4 * L::V_SLAB, Jg + e0 * 4, 4 * kCH * 8, bar);
-      }
+      tma_load_3d(s, map_v, 0, (int)(chunk * (kCH / 2)), 0, bar);                // v[4][16 el][15]
+      if (FE) tma_load_2d(s + 4 * L::V_SLAB, map_j, (int)e0, 0, bar);            // Jface[4][16 el]
+      else    tma_load_2d(s + 4 * L::V_SLAB, map_j, 0, (int)(chunk * (kCH / 2)), bar);   // J[16 el][4]
     }
   } else {
     const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
@@ -553,8 +525,8 @@ __device__ __forceinline__ void lift_issue(double* s, uint64_t* bar, const doubl
 
 template <int NW, bool FE>
 __global__ void __launch_bounds__(NW * 32, 1)
-k_lift_dmma(const double* __restrict__ Jg, const double* __restrict__ Og, OpmatRows rows, int nrows,
-            long long E, int tma_ok, int stagger) {
+k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg,
+            const double* __restrict__ Og, const __grid_constant__ OpmatRows rows, int nrows, long long E, int flags) {
   using L = LiftLayout;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sB = reinterpret_cast<double*>(smem_raw);
@@ -592,11 +564,12 @@ k_lift_dmma(const double* __restrict__ Jg, const double* __restrict__ Og, OpmatR
   WorkIter wi = work_iter(NW, nchunks * nrows);      // item = chunk * nrows + field
   const int g = lane >> 2, t = lane & 3;
 
+  const bool tma = flags & kFlagTma;
   if (wi.item < wi.nitems) {
     const long long c = wi.item / nrows;
-    lift_issue<FE>(s, bar, Jg, static_cast<const double*>(rows.field[wi.item - c * nrows]), c, E, tma_ok, lane);
+    const int fld = (int)(wi.item - c * nrows);
+    lift_issue<FE>(s, bar, &maps.in[fld], &maps.jac, Jg, static_cast<const double*>(rows.field[fld]), c, E, tma, lane);
   }
-  stagger_start(stagger, warp);
   for (uint32_t n = 0; wi.item < wi.nitems; wi.item += wi.stride, ++n) {
     mbar_wait(bar, n & 1u);
     double a[kME][L::KT];
@@ -616,7 +589,8 @@ k_lift_dmma(const double* __restrict__ Jg, const double* __restrict__ Og, OpmatR
       const long long nx = wi.item + wi.stride;
       if (nx < wi.nitems) {
         const long long c = nx / nrows;
-        lift_issue<FE>(s, bar, Jg, static_cast<const double*>(rows.field[nx - c * nrows]), c, E, tma_ok, lane);
+        const int fld = (int)(nx - c * nrows);
+        lift_issue<FE>(s, bar, &maps.in[fld], &maps.jac, Jg, static_cast<const double*>(rows.field[fld]), c, E, tma, lane);
       }
     }
 
@@ -668,8 +642,11 @@ k_lift_dmma(const double* __restrict__ Jg, const double* __restrict__ Og, OpmatR
     }
     fence_proxy_async();
     __syncwarp();
-    flush_block(outg + e0 * 35, stage, e0, E, tma_ok, lane);
-    if (lane == 0) tma_store_commit();
+    if (tma) {
+      if (lane == 0) { tma_store_2d(&maps.out[fld], stage, 0, (int)(c * (kCH / 2))); tma_store_commit(); }
+    } else {
+      flush_plain(outg + e0 * 35, stage, e0, E, lane);
+    }
   }
   if (lane == 0) tma_store_wait_all();
 }
@@ -688,6 +665,54 @@ static int set_smem(K kernel, size_t smem) {
   return e == cudaSuccess ? FNSM_OK : (int)e;
 }
 
+// cuTensorMapEncodeTiled, fetched through the runtime (the library links cudart only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// fp64 tensor map of rank 2 or 3; dims / box innermost first, strides (bytes) of dims 1..rank-1
+static bool make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
+                     const cuuint64_t* strides, const cuuint32_t* box) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint32_t ones[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+             ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// (E, W) row-major with W*2 doubles per element pair: box = 8 pairs = one 16-element chunk
+static bool map_rows(CUtensorMap* tm, const void* base, long long E, int W) {
+  const cuuint64_t dims[2] = {(cuuint64_t)(2 * W), (cuuint64_t)(E / 2)};
+  const cuuint64_t strides[1] = {(cuuint64_t)(16 * W)};
+  const cuuint32_t box[2] = {(cuuint32_t)(2 * W), (cuuint32_t)(kCH / 2)};
+  return make_map(tm, base, 2, dims, strides, box);
+}
+// (S, E, W): S slabs of (E, W)
+static bool map_slabs(CUtensorMap* tm, const void* base, long long E, int W, int S) {
+  const cuuint64_t dims[3] = {(cuuint64_t)(2 * W), (cuuint64_t)(E / 2), (cuuint64_t)S};
+  const cuuint64_t strides[2] = {(cuuint64_t)(16 * W), (cuuint64_t)E * W * 8};
+  const cuuint32_t box[3] = {(cuuint32_t)(2 * W), (cuuint32_t)(kCH / 2), (cuuint32_t)S};
+  return make_map(tm, base, 3, dims, strides, box);
+}
+// (R, E): R rows with the element axis contiguous
+static bool map_erows(CUtensorMap* tm, const void* base, long long E, int R) {
+  const cuuint64_t dims[2] = {(cuuint64_t)E, (cuuint64_t)R};
+  const cuuint64_t strides[1] = {(cuuint64_t)E * 8};
+  const cuuint32_t box[2] = {(cuuint32_t)kCH, (cuuint32_t)R};
+  return make_map(tm, base, 2, dims, strides, box);
+}
+
 template <int NW>
 static int launch_dmma_nw(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows,
                           long long E, const fnsm_cfg* cfg, const DevInfo& di, cudaStream_t st) {
@@ -695,12 +720,11 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
   const double* J = static_cast<const double*>(jac);
   const double* O = static_cast<const double*>(op);
   constexpr int threads = NW * 32;
-  int tma_ok = (E % 2 == 0) && aligned16(jac);
-  for (int r = 0; r < nrows; ++r) tma_ok = tma_ok && aligned16(rows.field[r]) && aligned16(rows.out[r]);
-  if (cfg && (cfg->reserved[0] & 1)) tma_ok = 0;    // debug flag: force the plain-load path
-  if (cfg && kind == FNSM_OP_DIV) tma_ok |= cfg->reserved[0] & 6;   // profiling aids: skip loads / stores
-  const int stagger = cfg ? cfg->reserved[1] : 0;   // start-up de-synchronisation, cycles per warp
-  if (stagger < 0 || stagger > (1 << 20)) return FNSM_E_BAD_CONFIG;
+  // TMA path: 16-B aligned bases and rows (E even); int32 box coordinates
+  bool tma = (E % 2 == 0) && E < (1LL << 31) - kCH && aligned16(jac);
+  for (int r = 0; r < nrows; ++r) tma = tma && aligned16(rows.field[r]) && aligned16(rows.out[r]);
+  const int dbg = cfg ? cfg->reserved[0] : 0;       // bit 0: force the plain path; bits 1, 2: profiling aids
+  if (dbg & 1) tma = false;
   auto grid_for_items = [&](long long nitems) {
     long long grid = di.sms;                          // one persistent CTA per SM
     const long long need = (nitems + NW - 1) / NW;
@@ -717,12 +741,17 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
     for (int r = 0; r < nrows; ++r) {
       const double* u = static_cast<const double*>(rows.field[r]);
       double* out = static_cast<double*>(rows.out[r]);
+      OpMaps maps;
+      bool ok = tma && map_erows(&maps.jac, J, E, 9);
+      if (is_div) ok = ok && map_slabs(&maps.in, u, E, 35, 3) && map_rows(&maps.out, out, E, 35);
+      else        ok = ok && map_rows(&maps.in, u, E, 35) && map_slabs(&maps.out, out, E, 35, 3);
+      const int flags = (ok ? kFlagTma : 0) | (dbg & (kFlagNoLoad | kFlagNoStore));
       if (is_div) {
         if (int rc = set_smem(k_div_dmma<NW>, smem)) return rc;
-        k_div_dmma<NW><<<grid_for_items(nchunks), threads, smem, st>>>(J, O, u, out, E, tma_ok, stagger);
+        k_div_dmma<NW><<<grid_for_items(nchunks), threads, smem, st>>>(maps, J, O, u, out, E, flags);
       } else {
         if (int rc = set_smem(k_grad_dmma<NW>, smem)) return rc;
-        k_grad_dmma<NW><<<grid_for_items(nchunks), threads, smem, st>>>(J, O, u, out, E, tma_ok, stagger);
+        k_grad_dmma<NW><<<grid_for_items(nchunks), threads, smem, st>>>(maps, J, O, u, out, E, flags);
       }
       if (int rc = post_launch()) return rc;
     }
@@ -731,12 +760,17 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
   const size_t smem = 8 * ((size_t)LiftLayout::B_DOUBLES + (size_t)NW * (LiftLayout::SLOT_DOUBLES + OUT_BLOCK)) + 8 * (size_t)NW;
   if (smem > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
   const unsigned grid = grid_for_items(nchunks * nrows);
+  LiftMaps maps;
+  bool ok = tma && (kind == FNSM_OP_LIFT_FE ? map_erows(&maps.jac, J, E, 4) : map_rows(&maps.jac, J, E, 4));
+  for (int r = 0; r < nrows && ok; ++r)
+    ok = map_slabs(&maps.in[r], rows.field[r], E, 15, 4) && map_rows(&maps.out[r], rows.out[r], E, 35);
+  const int flags = ok ? kFlagTma : 0;
   if (kind == FNSM_OP_LIFT_FE) {
     if (int rc = set_smem(k_lift_dmma<NW, true>, smem)) return rc;
-    k_lift_dmma<NW, true><<<grid, threads, smem, st>>>(J, O, rows, nrows, E, tma_ok, stagger);
+    k_lift_dmma<NW, true><<<grid, threads, smem, st>>>(maps, J, O, rows, nrows, E, flags);
   } else {
     if (int rc = set_smem(k_lift_dmma<NW, false>, smem)) return rc;
-    k_lift_dmma<NW, false><<<grid, threads, smem, st>>>(J, O, rows, nrows, E, tma_ok, stagger);
+    k_lift_dmma<NW, false><<<grid, threads, smem, st>>>(maps, J, O, rows, nrows, E, flags);
   }
   return post_launch();
 }

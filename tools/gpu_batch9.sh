@@ -1,0 +1,15 @@
+#!/bin/bash
+cd /root/repo
+mkdir -p gpurun_out
+run() { local name=$1 w=$2; shift 2; local extra=""; for kv in "$@"; do extra="$extra --param $kv"; done
+  timeout 300 python bench.py --workload $w --steps 10 --warmup 3 --no-e2e --no-cpu $extra > gpurun_out/b9_${name}.json 2> gpurun_out/b9_${name}.err; }
+for th in 256 320; do for f in 0 16 18 20; do run grad_${th}_f$f grad_p4 threads=$th flags=$f; done; done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/b9_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, 'ms=%.3f'%d['ms_per_step'], 'GF=%.0f'%d['value'], 'roof=%.3f'%d['roofline']['roofline_frac'])
+    except Exception as e:
+        print(f, 'ERR', e, open(f.replace('.json','.err')).read()[-200:])
+PY
