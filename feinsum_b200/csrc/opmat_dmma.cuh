@@ -142,16 +142,21 @@ constexpr int kFlagTma = 1;        // operands qualify for the TMA path
 constexpr int kFlagNoLoad = 2;     // profiling aid: skip loads  (results invalid)
 constexpr int kFlagNoStore = 4;    // profiling aid: skip stores (results invalid)
 
-struct WorkIter {
-  long long item, stride, nitems;
+// CTA-local dynamic work distribution: CTA b owns the items b, b + G, b + 2G, ...; its warps draw
+// the next k from a shared-memory counter, so a sub-partition hosting fewer warps (NW not a
+// multiple of 4) or a warp that was delayed simply takes fewer items.
+struct WorkQueue {
+  unsigned* ctr;
+  long long nitems;
+  __device__ __forceinline__ long long item_of(unsigned k) const {
+    return (long long)blockIdx.x + (long long)k * gridDim.x;
+  }
+  __device__ __forceinline__ unsigned ticket(int lane) const {      // valid in lane 0 only
+    return lane == 0 ? atomicAdd(ctr, 1u) : 0u;
+  }
+  __device__ __forceinline__ long long resolve(unsigned tk) const { return item_of(__shfl_sync(0xffffffffu, tk, 0)); }
+  __device__ __forceinline__ long long take(int lane) const { return resolve(ticket(lane)); }
 };
-__device__ __forceinline__ WorkIter work_iter(int nw, long long nitems) {
-  WorkIter w;
-  w.item = (long long)blockIdx.x * nw + uniform_warp_idx();
-  w.stride = (long long)gridDim.x * nw;
-  w.nitems = nitems;
-  return w;
-}
 
 // ================================================================= DIV =====
 // out[e,i] = sum_{r,j} D[r,i,j] * w[r,e,j],   w[r,e,j] = sum_x J[x,r,e] u[x,e,j]
@@ -218,8 +223,10 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
     const int jq = kt / 3, r = kt - 3 * jq, j = 4 * jq + t;
     sL[idx] = (d < kNL && j < 35) ? Dg[(r * 35 + 32 + d) * 35 + j] : 0.0;
   }
+  unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
     for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
+    *work_ctr = 0u;
     mbar_fence_init();
   }
   __syncthreads();
@@ -229,12 +236,13 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   uint64_t* bar = &bars[warp];
   const double* sJ = s + 3 * L::U_SLAB;
   const long long nchunks = (E + kCH - 1) / kCH;
-  WorkIter wi = work_iter(NW, nchunks);
+  const WorkQueue wq{work_ctr, nchunks};
   const int g = lane >> 2, t = lane & 3;
 
   const bool tma = flags & kFlagTma, dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
-  if (wi.item < wi.nitems && !dbg_noload) div_issue(s, bar, &maps, Jg, ug, wi.item, E, tma, lane);
-  for (uint32_t n = 0; wi.item < wi.nitems; wi.item += wi.stride, ++n) {
+  long long cur = wq.take(lane), nxt = wq.take(lane);
+  if (cur < nchunks && !dbg_noload) div_issue(s, bar, &maps, Jg, ug, cur, E, tma, lane);
+  for (uint32_t n = 0; cur < nchunks; ++n) {
     if (!dbg_noload) mbar_wait(bar, n & 1u);
     // ---- slot -> A fragments (Jacobian folded in) ----
     double a[kME][L::KT];
@@ -259,8 +267,8 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
       }
     }
     __syncwarp();                                  // every lane is done reading the slot
-    if (wi.item + wi.stride < wi.nitems && !dbg_noload)
-      div_issue(s, bar, &maps, Jg, ug, wi.item + wi.stride, E, tma, lane);
+    if (nxt < nchunks && !dbg_noload) div_issue(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
+    const unsigned tk = wq.ticket(lane);          // ticket after next; its latency hides under the DMMAs
 
     // ---- DMMA stream ----
     double acc[kME][kNT][2];
@@ -291,7 +299,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
       }
     }
     // ---- stage the [16][35] block, then one bulk store ----
-    const long long e0 = wi.item * kCH;
+    const long long e0 = cur * kCH;
     if (lane == 0) tma_store_wait_read();          // previous block has left the stage
     __syncwarp();
 #pragma unroll
@@ -310,11 +318,13 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
     __syncwarp();
     if (!dbg_nostore) {
       if (tma) {
-        if (lane == 0) { tma_store_2d(&maps.out, stage, 0, (int)(wi.item * (kCH / 2))); tma_store_commit(); }
+        if (lane == 0) { tma_store_2d(&maps.out, stage, 0, (int)(cur * (kCH / 2))); tma_store_commit(); }
       } else {
         flush_plain(outg + e0 * 35, stage, e0, E, lane);
       }
     }
+    cur = nxt;
+    nxt = wq.resolve(tk);
   }
   if (lane == 0) tma_store_wait_all();
 }
@@ -422,8 +432,10 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
     const int v = 2 * tile + (c & 1), i = 9 * (c >> 1) + v / 3, r = v % 3, j = 4 * kt + t;
     sB[idx] = (v < 27 && i < 35 && j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
   }
+  unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
     for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
+    *work_ctr = 0u;
     mbar_fence_init();
   }
   __syncthreads();
@@ -433,12 +445,13 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
   uint64_t* bar = &bars[warp];
   const double* sJ = s + L::U_SLAB;
   const long long nchunks = (E + kCH - 1) / kCH;
-  WorkIter wi = work_iter(NW, nchunks);
+  const WorkQueue wq{work_ctr, nchunks};
   const int g = lane >> 2, t = lane & 3;
 
   const bool tma = flags & kFlagTma, dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
-  if (wi.item < wi.nitems && !dbg_noload) grad_issue(s, bar, &maps, Jg, ug, wi.item, E, tma, lane);
-  for (uint32_t n = 0; wi.item < wi.nitems; wi.item += wi.stride, ++n) {
+  long long cur = wq.take(lane), nxt = wq.take(lane);
+  if (cur < nchunks && !dbg_noload) grad_issue(s, bar, &maps, Jg, ug, cur, E, tma, lane);
+  for (uint32_t n = 0; cur < nchunks; ++n) {
     if (!dbg_noload) mbar_wait(bar, n & 1u);
     double a[kME][L::KT];
     double Jr[kME][9];
@@ -455,10 +468,10 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
       for (int xr = 0; xr < 9; ++xr) Jr[m][xr] = sJ[xr * kCH + el];
     }
     __syncwarp();
-    if (wi.item + wi.stride < wi.nitems && !dbg_noload)
-      grad_issue(s, bar, &maps, Jg, ug, wi.item + wi.stride, E, tma, lane);
+    if (nxt < nchunks && !dbg_noload) grad_issue(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
+    const unsigned tk = wq.ticket(lane);
 
-    const long long e0 = wi.item * kCH;
+    const long long e0 = cur * kCH;
     grad_group<0, 3>(sB, a, Jr, stage, g, t, lane);
     grad_group<3, 3>(sB, a, Jr, stage, g, t, lane);
     grad_group<6, 3>(sB, a, Jr, stage, g, t, lane);
@@ -468,13 +481,15 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
     __syncwarp();
     if (!dbg_nostore) {
       if (tma) {
-        if (lane == 0) { tma_store_3d(&maps.out, stage, 0, (int)(wi.item * (kCH / 2)), 0); tma_store_commit(); }
+        if (lane == 0) { tma_store_3d(&maps.out, stage, 0, (int)(cur * (kCH / 2)), 0); tma_store_commit(); }
       } else {
 #pragma unroll
         for (int x = 0; x < 3; ++x)
           flush_plain(outg + ((long long)x * E + e0) * 35, stage + x * OUT_BLOCK, e0, E, lane);
       }
     }
+    cur = nxt;
+    nxt = wq.resolve(tk);
   }
   if (lane == 0) tma_store_wait_all();
 }
@@ -550,8 +565,10 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
     if (d < kNL) v = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
     sL[idx] = v;
   }
+  unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
     for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
+    *work_ctr = 0u;
     mbar_fence_init();
   }
   __syncthreads();
@@ -561,38 +578,51 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
   uint64_t* bar = &bars[warp];
   const double* sJ = s + 4 * L::V_SLAB;
   const long long nchunks = (E + kCH - 1) / kCH;
-  WorkIter wi = work_iter(NW, nchunks * nrows);      // item = chunk * nrows + field
+  // work unit of the queue = one chunk; the warp then walks the chunk's fields (items)
+  const WorkQueue wq{work_ctr, nchunks};
   const int g = lane >> 2, t = lane & 3;
 
   const bool tma = flags & kFlagTma;
-  if (wi.item < wi.nitems) {
-    const long long c = wi.item / nrows;
-    const int fld = (int)(wi.item - c * nrows);
-    lift_issue<FE>(s, bar, &maps.in[fld], &maps.jac, Jg, static_cast<const double*>(rows.field[fld]), c, E, tma, lane);
-  }
-  for (uint32_t n = 0; wi.item < wi.nitems; wi.item += wi.stride, ++n) {
+  long long cur = wq.take(lane), nxt = wq.take(lane);
+  int fld = 0;
+  if (cur < nchunks)
+    lift_issue<FE>(s, bar, &maps.in[0], &maps.jac, Jg, static_cast<const double*>(rows.field[0]), cur, E, tma, lane);
+  for (uint32_t n = 0; cur < nchunks; ++n) {
     mbar_wait(bar, n & 1u);
     double a[kME][L::KT];
 #pragma unroll
     for (int m = 0; m < kME; ++m) {
       const int el = chunk_el(g, m);
+      double Jf[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) Jf[f] = FE ? sJ[f * kCH + el] : sJ[el * 4 + f];
+      const double* sv = s + el * 15 + t;
 #pragma unroll
       for (int kt = 0; kt < L::KT; ++kt) {
-        // k = 4kt + t = 15 f + j ; f and j depend on the lane (t)
-        const int k = 4 * kt + t, f = k / 15, j = k - 15 * f;
-        const double jf = FE ? sJ[f * kCH + el] : sJ[el * 4 + f];
-        a[m][kt] = jf * s[f * L::V_SLAB + el * 15 + j];
+        // k = 4kt + t = 15 f + j: f = F0 for t < THR, F0 + 1 above (THR >= 4: the tile does not straddle a face)
+        const int F0 = (4 * kt) / 15, THR = 15 * (F0 + 1) - 4 * kt;
+        // address of v[f][el][j] = f*V_SLAB + el*15 + (k - 15 f) = el*15 + t + 4kt + (V_SLAB - 15) f
+        const int off0 = 4 * kt + (L::V_SLAB - 15) * F0;
+        double jf = Jf[F0], v;
+        if (THR < 4) {
+          const bool up = t >= THR;
+          v = sv[off0 + (up ? (L::V_SLAB - 15) : 0)];
+          jf = up ? Jf[F0 + 1 < 4 ? F0 + 1 : 3] : jf;
+        } else {
+          v = sv[off0];
+        }
+        a[m][kt] = jf * v;
       }
     }
     __syncwarp();
-    {
-      const long long nx = wi.item + wi.stride;
-      if (nx < wi.nitems) {
-        const long long c = nx / nrows;
-        const int fld = (int)(nx - c * nrows);
-        lift_issue<FE>(s, bar, &maps.in[fld], &maps.jac, Jg, static_cast<const double*>(rows.field[fld]), c, E, tma, lane);
-      }
-    }
+    // next item: next field of this chunk, else field 0 of the next chunk
+    const bool advance = fld + 1 == nrows;
+    const int nfld = advance ? 0 : fld + 1;
+    const long long nchunk = advance ? nxt : cur;
+    if (nchunk < nchunks)
+      lift_issue<FE>(s, bar, &maps.in[nfld], &maps.jac, Jg, static_cast<const double*>(rows.field[nfld]), nchunk, E, tma, lane);
+    unsigned tk = 0;
+    if (advance) tk = wq.ticket(lane);
 
     double acc[kME][kNT][2];
     double accL[2][kME][kNL];      // two partial sums per value: DFMA latency >> 6 chains
@@ -622,8 +652,7 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
       }
     }
 
-    const long long c = wi.item / nrows;
-    const int fld = (int)(wi.item - c * nrows);
+    const long long c = cur;
     const long long e0 = c * kCH;
     double* outg = static_cast<double*>(rows.out[fld]);
     if (lane == 0) tma_store_wait_read();
@@ -647,6 +676,8 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
     } else {
       flush_plain(outg + e0 * 35, stage, e0, E, lane);
     }
+    if (advance) { cur = nxt; nxt = wq.resolve(tk); }
+    fld = nfld;
   }
   if (lane == 0) tma_store_wait_all();
 }
@@ -727,7 +758,7 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
   if (dbg & 1) tma = false;
   auto grid_for_items = [&](long long nitems) {
     long long grid = di.sms;                          // one persistent CTA per SM
-    const long long need = (nitems + NW - 1) / NW;
+    const long long need = (nitems + NW - 1) / NW;      // no more CTAs than can be kept busy
     return (unsigned)(grid < need ? grid : need);
   };
 
@@ -736,7 +767,7 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
     const size_t slot_d = is_div ? DivLayout::SLOT_DOUBLES : GradLayout::SLOT_DOUBLES;
     const size_t b_d = is_div ? DivLayout::B_DOUBLES : GradLayout::B_DOUBLES;
     const size_t stage_d = is_div ? OUT_BLOCK : 3 * OUT_BLOCK;
-    const size_t smem = 8 * (b_d + (size_t)NW * (slot_d + stage_d)) + 8 * (size_t)NW;
+    const size_t smem = 8 * (b_d + (size_t)NW * (slot_d + stage_d)) + 8 * (size_t)NW + 8;
     if (smem > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
     for (int r = 0; r < nrows; ++r) {
       const double* u = static_cast<const double*>(rows.field[r]);
@@ -757,9 +788,9 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
     }
     return FNSM_OK;
   }
-  const size_t smem = 8 * ((size_t)LiftLayout::B_DOUBLES + (size_t)NW * (LiftLayout::SLOT_DOUBLES + OUT_BLOCK)) + 8 * (size_t)NW;
+  const size_t smem = 8 * ((size_t)LiftLayout::B_DOUBLES + (size_t)NW * (LiftLayout::SLOT_DOUBLES + OUT_BLOCK)) + 8 * (size_t)NW + 8;
   if (smem > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
-  const unsigned grid = grid_for_items(nchunks * nrows);
+  const unsigned grid = grid_for_items(nchunks);
   LiftMaps maps;
   bool ok = tma && (kind == FNSM_OP_LIFT_FE ? map_erows(&maps.jac, J, E, 4) : map_rows(&maps.jac, J, E, 4));
   for (int r = 0; r < nrows && ok; ++r)
@@ -781,12 +812,17 @@ static int launch_dmma(int kind, const void* jac, const void* op, const OpmatRow
   (void)n_outer; (void)ni; (void)nj;
   if (cfg && cfg->ctas_per_sm > 1) return FNSM_E_BAD_CONFIG;
   if (cfg && (cfg->stages < 0 || cfg->stages > 1)) return FNSM_E_BAD_CONFIG;
-  const int threads = (cfg && cfg->threads != 0) ? cfg->threads : 256;
+  // defaults from the round-1 sweep on B200 (profiles/): grad/div 10 warps, lift 12
+  const int dflt = (kind == FNSM_OP_GRAD || kind == FNSM_OP_DIV) ? 320 : 384;
+  const int threads = (cfg && cfg->threads != 0) ? cfg->threads : dflt;
   switch (threads) {
     case 128: return launch_dmma_nw<4>(kind, jac, op, rows, nrows, E, cfg, di, st);
     case 256: return launch_dmma_nw<8>(kind, jac, op, rows, nrows, E, cfg, di, st);
+    case 288: return launch_dmma_nw<9>(kind, jac, op, rows, nrows, E, cfg, di, st);
     case 320: return launch_dmma_nw<10>(kind, jac, op, rows, nrows, E, cfg, di, st);
+    case 352: return launch_dmma_nw<11>(kind, jac, op, rows, nrows, E, cfg, di, st);
     case 384: return launch_dmma_nw<12>(kind, jac, op, rows, nrows, E, cfg, di, st);
+    case 448: return launch_dmma_nw<14>(kind, jac, op, rows, nrows, E, cfg, di, st);
     default: return FNSM_E_BAD_CONFIG;
   }
 }
