@@ -31,3 +31,23 @@ from feinsum_b200.make_einsum import array, batched_einsum, einsum
 from feinsum_b200.utils import IndexNameGenerator
 
 __version__ = "2025.3+b200.r1"
+
+# codegen / measure entry points (reference src/feinsum/__init__.py:37-68); imported lazily so
+# that building the front-end objects does not need torch or the CUDA library
+_LAZY = {
+    "generate_cuda": "feinsum_b200.codegen.cuda",
+    "CudaProgram": "feinsum_b200.codegen.cuda",
+    "timeit": "feinsum_b200.measure",
+    "measure_giga_op_rate": "feinsum_b200.measure",
+    "get_roofline_flop_rate": "feinsum_b200.measure",
+    "stringify_comparison_vs_roofline": "feinsum_b200.measure",
+    "validate_batched_einsum_transform": "feinsum_b200.measure",
+}
+
+
+def __getattr__(name: str):
+    if name in _LAZY:
+        import importlib
+
+        return getattr(importlib.import_module(_LAZY[name]), name)
+    raise AttributeError(f"module 'feinsum_b200' has no attribute '{name}'")
