@@ -37,6 +37,8 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+METRIC = "GFLOP/s per DG einsum (opt_einsum-path flops), with HBM GB/s and % of B200 roofline"
+
 WORKLOADS = {
     # name: (builder name in this file, default E per GPU, description)
     "div_p4": ("DG divergence xre,rij,xej->ei p=4 tets fp64", 4_000_000),
@@ -44,6 +46,10 @@ WORKLOADS = {
     "lift_p4": ("DG face-mass lift ifj,fe,fej->ei b=4 p=4 tets fp64", 4_000_000),
     "tp_p7": ("tensor-product eabc,ia->eibc p=7 hexes fp64", 4_000_000),
     "div_p4_f32": ("DG divergence xre,rij,xej->ei p=4 tets fp32", 4_000_000),
+    "grad_p4_f32": ("DG gradient xre,rij,ej->xei p=4 tets fp32", 4_000_000),
+    "lift_p4_f32": ("DG face-mass lift ifj,fe,fej->ei b=4 p=4 tets fp32", 4_000_000),
+    "wave_p4": ("wave_3d_p4 operator: div(v) + grad(u) + 4-field lift in one call, fp64", 4_000_000),
+    "wave_p4_f32": ("wave_3d_p4 operator: div(v) + grad(u) + 4-field lift in one call, fp32", 4_000_000),
 }
 
 
@@ -65,6 +71,8 @@ def build_einsum(name: str):
               f.array(f"F_{k}", (4, "E", 15), dt)] for k in range(4)])
     if base == "tp_p7":
         return f.einsum("eabc,ia->eibc", f.array("A", ("E", 8, 8, 8), dt), f.array("M", (8, 8), dt))
+    if base == "wave_p4":
+        return None          # three einsums behind one call: see feinsum_b200/wave3d.py
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -153,6 +161,19 @@ def cpu_reference_leg(einsum, flops_per_elem: float, sample_e: int, steps: int, 
     return flops_per_elem * sample_e / dt * 1e-9, cores, dt * 1e3
 
 
+def cpu_reference_leg_wave(dtype: str, sample_e: int, steps: int, warmup: int):
+    """CPU port of the wave operator = its three loop nests run one after the other."""
+    from feinsum_b200 import measure, wave3d
+
+    secs = 0.0
+    cores = 1
+    for e in wave3d.wave3d_einsums("float32" if dtype == "f32" else "float64").values():
+        fl = sum(measure.get_flops_per_dtype(e, 1_000_000).values()) / 1e6
+        gf, cores, _ = cpu_reference_leg(e, fl, sample_e, steps, warmup)
+        secs += fl * sample_e / (gf * 1e9)
+    return wave3d.FLOPS_PER_ELEMENT * sample_e / secs * 1e-9, cores, secs * 1e3
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -177,12 +198,19 @@ def main() -> None:
     from feinsum_b200 import measure
 
     einsum = build_einsum(args.workload)
+    is_wave = einsum is None
     descr, default_e = WORKLOADS[args.workload]
     E = args.elements or default_e
-    flops_per_elem = sum(measure.get_flops_per_dtype(einsum, 1_000_000).values()) / 1e6
-    bytes_per_elem = (measure.get_footprint_bytes(einsum, 2_000_000)
-                      - measure.get_footprint_bytes(einsum, 1_000_000)) / 1e6
     dtype = "f32" if args.workload.endswith("_f32") else "f64"
+    if is_wave:
+        from feinsum_b200 import wave3d
+
+        flops_per_elem = float(wave3d.FLOPS_PER_ELEMENT)
+        bytes_per_elem = float(wave3d.BYTES_PER_ELEMENT[np.dtype("float32" if dtype == "f32" else "float64")])
+    else:
+        flops_per_elem = sum(measure.get_flops_per_dtype(einsum, 1_000_000).values()) / 1e6
+        bytes_per_elem = (measure.get_footprint_bytes(einsum, 2_000_000)
+                          - measure.get_footprint_bytes(einsum, 1_000_000)) / 1e6
     config = {
         "workload": f"{descr}, {E} elements per GPU (BASELINE configs[1] family)",
         "elements_per_gpu": E,
@@ -197,9 +225,12 @@ def main() -> None:
         if rank != 0:
             return
         sample_e = 400_000
-        gf, cores, ms = cpu_reference_leg(einsum, flops_per_elem, sample_e, args.steps, args.warmup)
+        if is_wave:
+            gf, cores, ms = cpu_reference_leg_wave(dtype, sample_e, args.steps, args.warmup)
+        else:
+            gf, cores, ms = cpu_reference_leg(einsum, flops_per_elem, sample_e, args.steps, args.warmup)
         line = {
-            "impl": "reference", "metric": "GFLOP/s per DG einsum (opt_einsum-path flops)",
+            "impl": "reference", "metric": METRIC,
             "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
@@ -224,6 +255,7 @@ def main() -> None:
     from feinsum_b200.codegen import generate_cuda
     from feinsum_b200.data import device_info
     from feinsum_b200.host_exec import HostExecutor, pinned_empty
+    from feinsum_b200 import wave3d
 
     dist = None
     if world > 1:
@@ -237,21 +269,26 @@ def main() -> None:
     cq = f.CudaQueue(local_rank)
     dev = cq.torch_device
 
-    prog = generate_cuda(einsum)
+    params = {k: int(v) for k, v in (kv.split("=") for kv in args.param)}
     if args.variant > 0:
-        prog = prog.with_params(variant=args.variant)
-    if args.param:
-        prog = prog.with_params(**{k: int(v) for k, v in (kv.split("=") for kv in args.param)})
-    ex = prog.executor(cq)
-
+        params["variant"] = args.variant
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     tdt = torch.float32 if dtype == "f32" else torch.float64
-    arrays = {
-        name: torch.rand(concrete(shape, E), dtype=tdt, device=dev, generator=gen)
-        for name, shape in sorted(einsum.arg_to_shape.items())
-    }
-    outs = {n: torch.zeros(concrete(einsum.shape, E), dtype=tdt, device=dev)
-            for n in einsum.output_names}
+    if is_wave:
+        prog = None
+        ex = wave3d.Wave3DExecutor(cq, "float32" if dtype == "f32" else "float64", **params)
+        in_shapes, out_shapes = wave3d.shapes(E)
+        kernel_id = "wave3d"
+    else:
+        prog = generate_cuda(einsum)
+        if params:
+            prog = prog.with_params(**params)
+        ex = prog.executor(cq)
+        in_shapes = {n: concrete(s, E) for n, s in sorted(einsum.arg_to_shape.items())}
+        out_shapes = {n: concrete(einsum.shape, E) for n in einsum.output_names}
+        kernel_id = prog.kernel_id
+    arrays = {n: torch.rand(s, dtype=tdt, device=dev, generator=gen) for n, s in sorted(in_shapes.items())}
+    outs = {n: torch.zeros(s, dtype=tdt, device=dev) for n, s in out_shapes.items()}
 
     def barrier():
         if dist is not None:
@@ -314,7 +351,43 @@ def main() -> None:
 
     # ---------------------------------------------------------------- e2e ---
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and is_wave:
+        # host buffers in, host buffers out, one stream: H2D of all ten operands, the fused
+        # call, D2H of the six results (no chunk pipelining for the three-einsum operator yet)
+        npdt = np.float32 if dtype == "f32" else np.float64
+        host_in = {n: pinned_empty(s, npdt) for n, s in in_shapes.items()}
+        for n in host_in:
+            torch.from_numpy(host_in[n]).copy_(arrays[n])
+        host_out = {n: pinned_empty(s, npdt) for n, s in out_shapes.items()}
+        dev_in = {n: torch.empty_like(a) for n, a in arrays.items()}
+
+        def e2e_step():
+            with torch.cuda.stream(cq.torch_stream):
+                for n in dev_in:
+                    dev_in[n].copy_(torch.from_numpy(host_in[n]), non_blocking=True)
+                ex(cq, **dev_in, **outs)
+                for n in host_out:
+                    torch.from_numpy(host_out[n]).copy_(outs[n], non_blocking=True)
+            cq.finish()
+
+        e2e_steps = 3
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": flops_per_elem * E * world / dt * 1e-9, "unit": "GFLOP/s",
+               "h2d_bytes_per_step": int(sum(a.nbytes for a in host_in.values())),
+               "d2h_bytes_per_step": int(sum(a.nbytes for a in host_out.values())),
+               "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "note": "pinned numpy in/out; H2D, fused call, D2H in order on one stream"}
+    elif not args.no_e2e:
         host_in = {}
         for name, shape in sorted(einsum.arg_to_shape.items()):
             h = pinned_empty(concrete(shape, E), np.float32 if dtype == "f32" else np.float64)
@@ -350,20 +423,23 @@ def main() -> None:
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sample_e = 400_000
-        gf, cores, ms = cpu_reference_leg(einsum, flops_per_elem, sample_e, 3, 1)
+        if is_wave:
+            gf, cores, ms = cpu_reference_leg_wave(dtype, sample_e, 3, 1)
+        else:
+            gf, cores, ms = cpu_reference_leg(einsum, flops_per_elem, sample_e, 3, 1)
         cpu = {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "port",
                "sample": f"{sample_e} elements x 3 steps of the C/OpenMP restatement of "
                          f"generate_loopy's loop nest ({ms:.1f} ms/step)"}
 
     if rank == 0:
         line = {
-            "metric": "GFLOP/s per DG einsum (opt_einsum-path flops), with HBM GB/s and % of B200 roofline",
+            "metric": METRIC,
             "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": config, "gbs": gbs, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "kernel": prog.kernel_id, "device": cq.device.name,
+            "kernel": kernel_id, "device": cq.device.name,
         }
         print(json.dumps(line))
     if dist is not None:
