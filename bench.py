@@ -147,7 +147,14 @@ def cpu_reference_leg(einsum, flops_per_elem: float, sample_e: int, steps: int, 
     from oracle import cgen, np_oracle
 
     cores = len(os.sched_getaffinity(0))
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # torchrun exports OMP_NUM_THREADS=1; this leg is meant to use every host core
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        import ctypes
+
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)   # if the runtime was initialised already
+    except OSError:
+        pass
     kern = cgen.CKernel(einsum)
     ins = np_oracle.generate_input_arrays(einsum, sample_e, 0)
     outs = [np.empty(s, dtype=np.result_type(*[a.dtype for a in row]))
