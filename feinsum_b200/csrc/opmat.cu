@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "opmat_simt.cuh"
 #include "opmat_dmma.cuh"
+#include "opmat_tf32.cuh"
 #include <cstdio>
 #include <cstring>
 
@@ -23,7 +24,7 @@ int opmat_cfg_space(int kernel_id, fnsm_cfg_range* out, int cap) {
   (void)kernel_id;
   fnsm_cfg_range tmp[5];
   int n = 0;
-  set_range(&tmp[n++], "variant", 0, 2, 1, 0);        // 0 = auto, 1 = dmma (fp64, p=4 shapes), 2 = simt
+  set_range(&tmp[n++], "variant", 0, 2, 1, 0);        // 0 = auto, 1 = tensor path (DMMA / 3xTF32, p=4 shapes), 2 = simt
   set_range(&tmp[n++], "tile_e", 8, 64, 8, 16);        // simt: elements per CTA tile
   set_range(&tmp[n++], "ctas_per_sm", 1, 8, 1, 0);     // persistent grid size
   set_range(&tmp[n++], "threads", 128, 448, 32, 0);   // dmma: 32 * warps per persistent CTA (4, 8..12, 14)
@@ -79,9 +80,10 @@ static int opmat_dispatch(int kind, int dtype, const void* jac, const void* op,
   if (int rc = device_info(&di)) return rc;
   int variant = cfg ? cfg->variant : 0;    // 0: library default
   if (variant < 0 || variant > 2) return FNSM_E_BAD_CONFIG;
-  const bool dmma_ok = dtype == FNSM_F64 && dmma_supported(kind, n_outer, ni, nj);
-  if (variant == 1 && !dmma_ok) return FNSM_E_UNSUPPORTED;
-  if (variant == 0) variant = dmma_ok ? 1 : 2;
+  // variant 1 = tensor path: fp64 DMMA, fp32 3xTF32 -- compiled for the p = 4 tet shapes
+  const bool tensor_ok = dmma_supported(kind, n_outer, ni, nj);
+  if (variant == 1 && !tensor_ok) return FNSM_E_UNSUPPORTED;
+  if (variant == 0) variant = tensor_ok ? 1 : 2;
   for (int r0 = 0; r0 < b; r0 += 8) {
     const int nr = (b - r0 < 8) ? (b - r0) : 8;
     OpmatRows rows{};
@@ -91,8 +93,10 @@ static int opmat_dispatch(int kind, int dtype, const void* jac, const void* op,
       if (!rows.field[r] || !rows.out[r]) return FNSM_E_BAD_ARG;
     }
     int rc;
-    if (variant == 1)
+    if (variant == 1 && dtype == FNSM_F64)
       rc = launch_dmma(kind, jac, op, rows, nr, n_outer, ni, nj, E, cfg, di, st);
+    else if (variant == 1)
+      rc = launch_tf32(kind, jac, op, rows, nr, E, cfg, di, st);
     else if (dtype == FNSM_F64)
       rc = launch_simt<double>(kind, jac, op, rows, nr, n_outer, ni, nj, E, cfg, di, st);
     else
@@ -133,7 +137,7 @@ extern "C" int fnsm_b200_wave3d_fused(int32_t dtype, const fnsm_wave_args* a, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == FNSM_F64 && (!cfg || cfg->variant != 2))
     return launch_wave3d_dmma(a, E, cfg, di, st);
-  // variant 2 / fp32: three back-to-back launches of the simt kernels on one stream
+  // variant 2 or fp32: three back-to-back launches through the per-einsum dispatch
   const void* f1[1] = {a->v}; void* o1[1] = {a->div_out};
   int rc = opmat_dispatch(FNSM_OP_DIV, dtype, a->J, a->D, f1, o1, 1, 3, 35, 35, E, cfg, st);
   if (rc) return rc;

@@ -67,7 +67,7 @@ enum {
  * Zero in any field = kernel default.
  */
 typedef struct fnsm_cfg {
-  int32_t variant;        /* 0 = auto, 1 = dmma (fp64 tensor path), 2 = simt          */
+  int32_t variant;        /* 0 = auto, 1 = tensor path (DMMA / 3xTF32), 2 = simt      */
   int32_t tile_e;         /* elements per CTA tile                                   */
   int32_t threads;        /* threads per CTA                                         */
   int32_t stages;         /* depth of the global->shared pipeline                    */

@@ -65,10 +65,25 @@ def test_lift_fp64(cq, n, variant, builder):
     check(builder(), n, cq, variant=variant)
 
 
-@pytest.mark.parametrize("n", [1, 17, 1001])
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("n", [1, 4, 17, 1000, 1001, 10008])
 @pytest.mark.parametrize("builder", [E.grad, E.div, E.lift_ef, E.lift_fe])
-def test_opmat_fp32(cq, n, builder):
-    check(builder(dtype="float32"), n, cq)
+def test_opmat_fp32(cq, n, builder, variant):
+    # variant 1 = 3xTF32 tensor path (TMA when n % 4 == 0, plain loads otherwise), 2 = simt
+    check(builder(dtype="float32"), n, cq, variant=variant)
+
+
+def test_fp32_tensor_path_accuracy_margin(cq):
+    """3xTF32 must sit well inside the fp32 north-star tolerance (1e-5): measure the actual
+    worst relative error of the tensor path against the fp64 oracle on 10 000 elements."""
+    for builder in (E.grad, E.div, E.lift_fe):
+        e = builder(dtype="float32")
+        ins = np_oracle.generate_input_arrays(e, 10000, 3)
+        got = run(e, ins, cq, variant=1)
+        ref = np_oracle.reference_outputs_fp64(e, ins)
+        for k in ref:
+            rel = np.max(np.abs(got[k].astype(np.float64) - ref[k]) / np.abs(ref[k]))
+            assert rel < 3e-6, (builder.__name__, k, rel)
 
 
 @pytest.mark.parametrize("n", [1, 100])
