@@ -42,6 +42,13 @@ _LAZY = {
     "get_roofline_flop_rate": "feinsum_b200.measure",
     "stringify_comparison_vs_roofline": "feinsum_b200.measure",
     "validate_batched_einsum_transform": "feinsum_b200.measure",
+    "canonicalize_einsum": "feinsum_b200.canonicalization",
+    "query": "feinsum_b200.sql_utils",
+    "retrieve": "feinsum_b200.sql_utils",
+    "record_facts": "feinsum_b200.sql_utils",
+    "get_timed_einsums_in_db": "feinsum_b200.sql_utils",
+    "DEFAULT_DB": "feinsum_b200.sql_utils",
+    "autotune": "feinsum_b200.tuning",
 }
 
 

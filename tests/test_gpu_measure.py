@@ -66,3 +66,34 @@ def test_measured_peaks(cq):
     assert 5_000 < fp64 < 100_000
     bw = _cabi.measure_peak(2)
     assert 1_000 < bw < 12_000
+
+
+def test_autotune_record_retrieve_on_device(cq, tmp_path):
+    """End to end on the GPU: search the grad launch space for a few points, then retrieve the best
+    configuration from the facts database and run it (reference test_tuple_args.py's flow)."""
+    import os
+
+    import torch
+
+    from feinsum_b200 import tuning
+    from feinsum_b200.codegen import generate_cuda
+    from oracle import np_oracle
+
+    db = str(tmp_path / "facts.sqlite")
+    mod = os.path.join(tuning._get_impls_path(), "xre_rij_ej_to_xei.py")
+    best = f.autotune(E.grad(), mod, cq, db_path=db, long_dim_length=20_000, test_limit=3)
+    facts = f.query(E.grad(), cq.device, database=db)
+    assert best is not None and 1 <= len(facts) <= 3
+    assert all(q.runtime_in_sec > 0 and q.giga_op_rate("float64") > 100 for q in facts)
+    transform = f.retrieve(E.grad(), cq.device, database=db)
+    prog = transform(generate_cuda(E.grad()), insn_match=None, kernel_name=None)
+    ins = np_oracle.generate_input_arrays(E.grad(), 1000)
+    dev = {k: torch.from_numpy(v).to(cq.torch_device) for k, v in ins.items()}
+    evt, outs = prog.executor(cq)(cq, **dev)
+    evt.wait()
+    np_oracle.assert_matches({k: v.cpu().numpy() for k, v in outs.items()},
+                             np_oracle.reference_outputs(E.grad(), ins), north_star=True)
+    # a second search only re-times what is not recorded yet
+    n_before = len(facts)
+    f.autotune(E.grad(), mod, cq, db_path=db, long_dim_length=20_000, test_limit=1)
+    assert len(f.query(E.grad(), cq.device, database=db)) <= n_before + 1
