@@ -181,6 +181,26 @@ def cpu_reference_leg_wave(dtype: str, sample_e: int, steps: int, warmup: int):
     return wave3d.FLOPS_PER_ELEMENT * sample_e / secs * 1e-9, cores, secs * 1e3
 
 
+def profiled_traffic(workload: str):
+    """DRAM bytes of one launch of the workload's kernel from the committed ncu capture
+    (profiles/rNN_ncu_<workload>.txt: dram__bytes_read.sum + dram__bytes_write.sum); None if absent."""
+    import glob
+    import re
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_ncu_{workload}.txt")))
+    if not files:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tot = 0.0
+    text = open(files[-1]).read()
+    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        m = re.search(rf"{re.escape(key)} = ([0-9.]+) (\w+)", text)
+        if not m:
+            return None, None
+        tot += float(m.group(1)) * unit.get(m.group(2), 1.0)
+    return tot, os.path.relpath(files[-1], ROOT)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -343,8 +363,9 @@ def main() -> None:
     else:
         roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach_gbs / hbm_peak}
+    traffic, traffic_src = (profiled_traffic(args.workload) if E == default_e and not params else (None, None))
     roof.update({
-        "traffic": None,
+        "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": (f"{'FP64 DMMA/DFMA' if dtype == 'f64' else 'FP32 FFMA2'} peak measured in this run by "
                         f"fnsm_b200_measure_peak (MEASURED_PEAKS.json has no {dtype} figure); "
                         f"HBM {hbm_peak} GB/s from {hbm_src}"),
