@@ -52,28 +52,24 @@ __device__ __forceinline__ void flush_plain32(float* __restrict__ dst, const flo
   for (int k = lane; k < ne * 35; k += 32) dst[k] = stage[k];
 }
 
-// fragment table: the operator in fp32, one float2 (k = t, k = t + 4) per lane and fragment.  The
-// hi / lo split of B happens in registers at use: the kernels are shared-memory-wavefront bound
-// (88 % of peak with separate hi and lo tables, profiles/r01_ncu_*_f32.txt) and have issue slots to spare.
+// fragment tables: operator split into hi / lo, one float2 (k = t, k = t + 4) per lane
 template <class F>
-__device__ __forceinline__ void fill_b_table(float2* tab, int n_frag, F value_at /* (frag, lane, half) */) {
+__device__ __forceinline__ void fill_b_tables(uint2* hi, uint2* lo, int n_frag, F value_at /* (frag, lane, half) */) {
   for (int idx = threadIdx.x; idx < n_frag * 32; idx += blockDim.x) {
     const int frag = idx >> 5, ln = idx & 31;
-    tab[idx] = make_float2(value_at(frag, ln, 0), value_at(frag, ln, 1));
+    uint2 h, l;
+    split_tf32(value_at(frag, ln, 0), h.x, l.x);
+    split_tf32(value_at(frag, ln, 1), h.y, l.y);
+    hi[idx] = h;
+    lo[idx] = l;
   }
-}
-__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], float2 b) {
-  uint2 bhi, blo;
-  split_tf32(b.x, bhi.x, blo.x);
-  split_tf32(b.y, bhi.y, blo.y);
-  mma_3xtf32(c, ahi, alo, bhi, blo);
 }
 
 // ================================================================= DIV =====
 // out[e,i] = sum_k B[k][i] w[e][k],  k = 35 r + j (105 -> 112),  w = sum_x J[x,r,e] u[x,e,j]
 struct Div32 {
   static constexpr int KT = 14, NT = 5;
-  static constexpr int B_BYTES = KT * NT * 32 * 8;
+  static constexpr int B_BYTES = 2 * KT * NT * 32 * 8;                  // hi + lo tables
   static constexpr int U_SLAB = kCH * 35;                               // floats per x
   static constexpr int J_OFF = align128(3 * U_SLAB * 4) / 4;            // J region (floats), 128-B aligned for TMA
   static constexpr int SLOT_BYTES_TX = (3 * U_SLAB + 9 * kCH) * 4;      // bytes the two TMA loads deliver
@@ -112,7 +108,8 @@ k_div_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, co
            const float* __restrict__ ug, float* __restrict__ outg, long long E, int flags) {
   using L = Div32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float2* sB = reinterpret_cast<float2*>(smem_raw);
+  uint2* sBhi = reinterpret_cast<uint2*>(smem_raw);
+  uint2* sBlo = sBhi + L::KT * L::NT * 32;
   unsigned char* slots = smem_raw + L::B_BYTES;
   unsigned char* stages = slots + (size_t)NW * L::SLOT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * L::STAGE_BYTES);
@@ -120,7 +117,7 @@ k_div_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, co
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   // fragment (kt, nt): lane (n = g, k = t / t + 4): D[r][8nt+g][j], 35 r + j = 8kt + t (+4)
-  fill_b_table(sB, L::KT * L::NT, [&](int frag, int ln, int half) {
+  fill_b_tables(sBhi, sBlo, L::KT * L::NT, [&](int frag, int ln, int half) {
     const int kt = frag / L::NT, nt = frag - kt * L::NT;
     const int g = ln >> 2, t = ln & 3, k = 8 * kt + t + 4 * half, i = 8 * nt + g;
     const int r = k / 35, j = k - 35 * r;
@@ -192,7 +189,8 @@ k_div_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, co
     for (int kt = 0; kt < L::KT; ++kt) {
 #pragma unroll
       for (int nt = 0; nt < L::NT; ++nt) {
-        mma_3xtf32(acc[nt], ahi[kt], alo[kt], sB[(kt * L::NT + nt) * 32 + lane]);
+        const uint2 bh = sBhi[(kt * L::NT + nt) * 32 + lane], bl = sBlo[(kt * L::NT + nt) * 32 + lane];
+        mma_3xtf32(acc[nt], ahi[kt], alo[kt], bh, bl);
       }
     }
     // ---- stage [16][35], one TMA store ----
@@ -223,7 +221,7 @@ k_div_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, co
 // column layout of the fp64 kernel);  out[x,e,i] = sum_r J[x,r,e] T[e][(i,r)]
 struct Grad32 {
   static constexpr int KT = 5, NTILE = 14;
-  static constexpr int B_BYTES = NTILE * KT * 32 * 8;
+  static constexpr int B_BYTES = 2 * NTILE * KT * 32 * 8;
   static constexpr int U_SLAB = kCH * 35;
   static constexpr int J_OFF = align128(U_SLAB * 4) / 4;
   static constexpr int SLOT_BYTES_TX = (U_SLAB + 9 * kCH) * 4;
@@ -255,7 +253,7 @@ __device__ __forceinline__ void grad32_issue(float* s, uint64_t* bar, const OpMa
 }
 
 template <int T0, int NTG>
-__device__ __forceinline__ void grad32_group(const float2* __restrict__ sB,
+__device__ __forceinline__ void grad32_group(const uint2* __restrict__ sBhi, const uint2* __restrict__ sBlo,
                                              const uint32_t (&ahi)[Grad32::KT][4], const uint32_t (&alo)[Grad32::KT][4],
                                              const float (&Jr)[2][9], float* stage, int g, int t, int lane) {
   using L = Grad32;
@@ -266,7 +264,8 @@ __device__ __forceinline__ void grad32_group(const float2* __restrict__ sB,
   for (int kt = 0; kt < L::KT; ++kt) {
 #pragma unroll
     for (int jt = 0; jt < NTG; ++jt) {
-      mma_3xtf32(acc[jt], ahi[kt], alo[kt], sB[((T0 + jt) * L::KT + kt) * 32 + lane]);
+      const int f = ((T0 + jt) * L::KT + kt) * 32 + lane;
+      mma_3xtf32(acc[jt], ahi[kt], alo[kt], sBhi[f], sBlo[f]);
     }
   }
   if (T0 == 0) {
@@ -300,7 +299,8 @@ k_grad_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, c
             const float* __restrict__ ug, float* __restrict__ outg, long long E, int flags) {
   using L = Grad32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float2* sB = reinterpret_cast<float2*>(smem_raw);
+  uint2* sBhi = reinterpret_cast<uint2*>(smem_raw);
+  uint2* sBlo = sBhi + L::NTILE * L::KT * 32;
   unsigned char* slots = smem_raw + L::B_BYTES;
   unsigned char* stages = slots + (size_t)NW * L::SLOT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * L::STAGE_BYTES);
@@ -308,7 +308,7 @@ k_grad_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, c
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   // fragment (tile, kt): column c = g holds value v = 2 tile + (c & 1) of lane c >> 1: (dof 9 (c>>1) + v/3, r = v%3)
-  fill_b_table(sB, L::NTILE * L::KT, [&](int frag, int ln, int half) {
+  fill_b_tables(sBhi, sBlo, L::NTILE * L::KT, [&](int frag, int ln, int half) {
     const int tile = frag / L::KT, kt = frag - tile * L::KT;
     const int c = ln >> 2, t = ln & 3, j = 8 * kt + t + 4 * half;
     const int v = 2 * tile + (c & 1), i = 9 * (c >> 1) + v / 3, r = v % 3;
@@ -358,11 +358,11 @@ k_grad_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, c
     const unsigned tk = wq.ticket(lane);
 
     const long long e0 = cur * kCH;
-    grad32_group<0, 3>(sB, ahi, alo, Jr, stage, g, t, lane);
-    grad32_group<3, 3>(sB, ahi, alo, Jr, stage, g, t, lane);
-    grad32_group<6, 3>(sB, ahi, alo, Jr, stage, g, t, lane);
-    grad32_group<9, 3>(sB, ahi, alo, Jr, stage, g, t, lane);
-    grad32_group<12, 2>(sB, ahi, alo, Jr, stage, g, t, lane);
+    grad32_group<0, 3>(sBhi, sBlo, ahi, alo, Jr, stage, g, t, lane);
+    grad32_group<3, 3>(sBhi, sBlo, ahi, alo, Jr, stage, g, t, lane);
+    grad32_group<6, 3>(sBhi, sBlo, ahi, alo, Jr, stage, g, t, lane);
+    grad32_group<9, 3>(sBhi, sBlo, ahi, alo, Jr, stage, g, t, lane);
+    grad32_group<12, 2>(sBhi, sBlo, ahi, alo, Jr, stage, g, t, lane);
     fence_proxy_async();
     __syncwarp();
     if (tma) {
@@ -382,7 +382,7 @@ k_grad_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, c
 // out_k[e,i] = sum_k Op(f,i,j) Jf(e,f) v_k[f,e,j],  k = 15 f + j (60 -> 64)
 struct Lift32 {
   static constexpr int KT = 8, NT = 5;
-  static constexpr int B_BYTES = KT * NT * 32 * 8;
+  static constexpr int B_BYTES = 2 * KT * NT * 32 * 8;
   static constexpr int V_SLAB = kCH * 15;                               // floats per face
   static constexpr int J_OFF = 4 * V_SLAB;                              // 3840 floats = 15360 B (128-B aligned)
   static constexpr int SLOT_BYTES_TX = (4 * V_SLAB + 4 * kCH) * 4;
@@ -426,14 +426,15 @@ k_lift_tf32(const __grid_constant__ LiftMaps maps, const float* __restrict__ Jg,
             const __grid_constant__ OpmatRows rows, int nrows, long long E, int flags) {
   using L = Lift32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float2* sB = reinterpret_cast<float2*>(smem_raw);
+  uint2* sBhi = reinterpret_cast<uint2*>(smem_raw);
+  uint2* sBlo = sBhi + L::KT * L::NT * 32;
   unsigned char* slots = smem_raw + L::B_BYTES;
   unsigned char* stages = slots + (size_t)NW * L::SLOT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * L::STAGE_BYTES);
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  fill_b_table(sB, L::KT * L::NT, [&](int frag, int ln, int half) {
+  fill_b_tables(sBhi, sBlo, L::KT * L::NT, [&](int frag, int ln, int half) {
     const int kt = frag / L::NT, nt = frag - kt * L::NT;
     const int g = ln >> 2, t = ln & 3, k = 8 * kt + t + 4 * half, i = 8 * nt + g;
     const int f = k / 15, j = k - 15 * f;
@@ -509,7 +510,8 @@ k_lift_tf32(const __grid_constant__ LiftMaps maps, const float* __restrict__ Jg,
     for (int kt = 0; kt < L::KT; ++kt) {
 #pragma unroll
       for (int nt = 0; nt < L::NT; ++nt) {
-        mma_3xtf32(acc[nt], ahi[kt], alo[kt], sB[(kt * L::NT + nt) * 32 + lane]);
+        const uint2 bh = sBhi[(kt * L::NT + nt) * 32 + lane], bl = sBlo[(kt * L::NT + nt) * 32 + lane];
+        mma_3xtf32(acc[nt], ahi[kt], alo[kt], bh, bl);
       }
     }
     const long long e0 = cur * kCH;
