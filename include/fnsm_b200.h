@@ -177,7 +177,10 @@ int fnsm_b200_query_cfg_space(int32_t kernel_id, fnsm_cfg_range* out, int32_t ca
  * src/feinsum/data/device_info.py:4-28 with measurements on the running box).
  *   which: 0 = FP64 FMA GFLOP/s, 1 = FP32 FMA GFLOP/s, 2 = HBM copy GB/s,
  *          3 = FP64 DMMA (mma.sync m8n8k4) GFLOP/s
- * Synchronous; runs a register-resident micro-kernel for a few milliseconds.
+ *   which + 16: the SUSTAINED figure -- the micro-kernel first runs for ~0.7 s so the board sits at
+ *          its power cap (FP64 tensor work pulls the B200's 1000 W limit and the SM clock drops);
+ *          use it as the roofline denominator of a kernel timed inside a long step.
+ * Synchronous; runs a register-resident micro-kernel for a few milliseconds (burst).
  * ---------------------------------------------------------------------- */
 int fnsm_b200_measure_peak(int32_t which, double* result);
 
