@@ -55,17 +55,23 @@ __device__ __forceinline__ void flush_plain32(float* __restrict__ dst, const flo
   for (int k = lane; k < ne * 35; k += 32) dst[k] = stage[k];
 }
 
-// fragment tables: operator split into hi / lo, one float2 (k = t, k = t + 4) per lane
+// fragment table: operator split into hi / lo, one uint4 {hi(k = t), hi(k = t + 4), lo(k = t), lo(k = t + 4)}
+// per lane and fragment -> a single conflict-free LDS.128 feeds the three MMAs of a product
 template <class F>
-__device__ __forceinline__ void fill_b_tables(uint2* hi, uint2* lo, int n_frag, F value_at /* (frag, lane, half) */) {
+__device__ __forceinline__ void fill_b_table(uint4* tab, int n_frag, F value_at /* (frag, lane, half) */) {
   for (int idx = threadIdx.x; idx < n_frag * 32; idx += blockDim.x) {
     const int frag = idx >> 5, ln = idx & 31;
-    uint2 h, l;
-    split_tf32(value_at(frag, ln, 0), h.x, l.x);
-    split_tf32(value_at(frag, ln, 1), h.y, l.y);
-    hi[idx] = h;
-    lo[idx] = l;
+    uint4 v;
+    split_tf32(value_at(frag, ln, 0), v.x, v.z);
+    split_tf32(value_at(frag, ln, 1), v.y, v.w);
+    tab[idx] = v;
   }
+}
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], float (&corr)[4], const uint32_t (&ahi)[4],
+                                           const uint32_t (&alo)[4], uint4 b) {
+  mma_tf32(corr, alo, b.x, b.y);
+  mma_tf32(corr, ahi, b.z, b.w);
+  mma_tf32(c, ahi, b.x, b.y);
 }
 
 // ================================================================= DIV =====
@@ -111,8 +117,7 @@ k_div_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, co
            const float* __restrict__ ug, float* __restrict__ outg, long long E, int flags) {
   using L = Div32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint2* sBhi = reinterpret_cast<uint2*>(smem_raw);
-  uint2* sBlo = sBhi + L::KT * L::NT * 32;
+  uint4* sB = reinterpret_cast<uint4*>(smem_raw);
   unsigned char* slots = smem_raw + L::B_BYTES;
   unsigned char* stages = slots + (size_t)NW * L::SLOT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * L::STAGE_BYTES);
@@ -120,7 +125,7 @@ k_div_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, co
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   // fragment (kt, nt): lane (n = g, k = t / t + 4): D[r][8nt+g][j], 35 r + j = 8kt + t (+4)
-  fill_b_tables(sBhi, sBlo, L::KT * L::NT, [&](int frag, int ln, int half) {
+  fill_b_table(sB, L::KT * L::NT, [&](int frag, int ln, int half) {
     const int kt = frag / L::NT, nt = frag - kt * L::NT;
     const int g = ln >> 2, t = ln & 3, k = 8 * kt + t + 4 * half, i = 8 * nt + g;
     const int r = k / 35, j = k - 35 * r;
@@ -194,8 +199,7 @@ k_div_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, co
     for (int kt = 0; kt < L::KT; ++kt) {
 #pragma unroll
       for (int nt = 0; nt < L::NT; ++nt) {
-        const uint2 bh = sBhi[(kt * L::NT + nt) * 32 + lane], bl = sBlo[(kt * L::NT + nt) * 32 + lane];
-        mma_3xtf32(acc[nt], corr[nt], ahi[kt], alo[kt], bh, bl);
+        mma_3xtf32(acc[nt], corr[nt], ahi[kt], alo[kt], sB[(kt * L::NT + nt) * 32 + lane]);
       }
     }
 #pragma unroll
@@ -262,7 +266,7 @@ __device__ __forceinline__ void grad32_issue(float* s, uint64_t* bar, const OpMa
 }
 
 template <int T0, int NTG>
-__device__ __forceinline__ void grad32_group(const uint2* __restrict__ sBhi, const uint2* __restrict__ sBlo,
+__device__ __forceinline__ void grad32_group(const uint4* __restrict__ sB,
                                              const uint32_t (&ahi)[Grad32::KT][4], const uint32_t (&alo)[Grad32::KT][4],
                                              const float (&Jr)[2][9], float* stage, int g, int t, int lane) {
   using L = Grad32;
@@ -275,8 +279,7 @@ __device__ __forceinline__ void grad32_group(const uint2* __restrict__ sBhi, con
   for (int kt = 0; kt < L::KT; ++kt) {
 #pragma unroll
     for (int jt = 0; jt < NTG; ++jt) {
-      const int f = ((T0 + jt) * L::KT + kt) * 32 + lane;
-      mma_3xtf32(acc[jt], corr[jt], ahi[kt], alo[kt], sBhi[f], sBlo[f]);
+      mma_3xtf32(acc[jt], corr[jt], ahi[kt], alo[kt], sB[((T0 + jt) * L::KT + kt) * 32 + lane]);
     }
   }
 #pragma unroll
@@ -314,8 +317,7 @@ k_grad_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, c
             const float* __restrict__ ug, float* __restrict__ outg, long long E, int flags) {
   using L = Grad32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint2* sBhi = reinterpret_cast<uint2*>(smem_raw);
-  uint2* sBlo = sBhi + L::NTILE * L::KT * 32;
+  uint4* sB = reinterpret_cast<uint4*>(smem_raw);
   unsigned char* slots = smem_raw + L::B_BYTES;
   unsigned char* stages = slots + (size_t)NW * L::SLOT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * L::STAGE_BYTES);
@@ -323,7 +325,7 @@ k_grad_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, c
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   // fragment (tile, kt): column c = g holds value v = 2 tile + (c & 1) of lane c >> 1: (dof 9 (c>>1) + v/3, r = v%3)
-  fill_b_tables(sBhi, sBlo, L::NTILE * L::KT, [&](int frag, int ln, int half) {
+  fill_b_table(sB, L::NTILE * L::KT, [&](int frag, int ln, int half) {
     const int tile = frag / L::KT, kt = frag - tile * L::KT;
     const int c = ln >> 2, t = ln & 3, j = 8 * kt + t + 4 * half;
     const int v = 2 * tile + (c & 1), i = 9 * (c >> 1) + v / 3, r = v % 3;
@@ -373,11 +375,11 @@ k_grad_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, c
     const unsigned tk = wq.ticket(lane);
 
     const long long e0 = cur * kCH;
-    grad32_group<0, 3>(sBhi, sBlo, ahi, alo, Jr, stage, g, t, lane);
-    grad32_group<3, 3>(sBhi, sBlo, ahi, alo, Jr, stage, g, t, lane);
-    grad32_group<6, 3>(sBhi, sBlo, ahi, alo, Jr, stage, g, t, lane);
-    grad32_group<9, 3>(sBhi, sBlo, ahi, alo, Jr, stage, g, t, lane);
-    grad32_group<12, 2>(sBhi, sBlo, ahi, alo, Jr, stage, g, t, lane);
+    grad32_group<0, 3>(sB, ahi, alo, Jr, stage, g, t, lane);
+    grad32_group<3, 3>(sB, ahi, alo, Jr, stage, g, t, lane);
+    grad32_group<6, 3>(sB, ahi, alo, Jr, stage, g, t, lane);
+    grad32_group<9, 3>(sB, ahi, alo, Jr, stage, g, t, lane);
+    grad32_group<12, 2>(sB, ahi, alo, Jr, stage, g, t, lane);
     fence_proxy_async();
     __syncwarp();
     if (tma) {
@@ -441,15 +443,14 @@ k_lift_tf32(const __grid_constant__ LiftMaps maps, const float* __restrict__ Jg,
             const __grid_constant__ OpmatRows rows, int nrows, long long E, int flags) {
   using L = Lift32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint2* sBhi = reinterpret_cast<uint2*>(smem_raw);
-  uint2* sBlo = sBhi + L::KT * L::NT * 32;
+  uint4* sB = reinterpret_cast<uint4*>(smem_raw);
   unsigned char* slots = smem_raw + L::B_BYTES;
   unsigned char* stages = slots + (size_t)NW * L::SLOT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * L::STAGE_BYTES);
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  fill_b_tables(sBhi, sBlo, L::KT * L::NT, [&](int frag, int ln, int half) {
+  fill_b_table(sB, L::KT * L::NT, [&](int frag, int ln, int half) {
     const int kt = frag / L::NT, nt = frag - kt * L::NT;
     const int g = ln >> 2, t = ln & 3, k = 8 * kt + t + 4 * half, i = 8 * nt + g;
     const int f = k / 15, j = k - 15 * f;
@@ -527,8 +528,7 @@ k_lift_tf32(const __grid_constant__ LiftMaps maps, const float* __restrict__ Jg,
     for (int kt = 0; kt < L::KT; ++kt) {
 #pragma unroll
       for (int nt = 0; nt < L::NT; ++nt) {
-        const uint2 bh = sBhi[(kt * L::NT + nt) * 32 + lane], bl = sBlo[(kt * L::NT + nt) * 32 + lane];
-        mma_3xtf32(acc[nt], corr[nt], ahi[kt], alo[kt], bh, bl);
+        mma_3xtf32(acc[nt], corr[nt], ahi[kt], alo[kt], sB[(kt * L::NT + nt) * 32 + lane]);
       }
     }
 #pragma unroll
@@ -647,7 +647,9 @@ static int launch_tf32(int kind, const void* jac, const void* op, const OpmatRow
                        long long E, const fnsm_cfg* cfg, const DevInfo& di, cudaStream_t st) {
   if (cfg && cfg->ctas_per_sm > 1) return FNSM_E_BAD_CONFIG;
   if (cfg && (cfg->stages < 0 || cfg->stages > 1)) return FNSM_E_BAD_CONFIG;
-  const int threads = (cfg && cfg->threads != 0) ? cfg->threads : 512;   // round-1 sweep: 16 warps best for all three
+  // round-1 sweep: 16 warps for grad / lift, 12 for div (its 112 A-fragment registers spill at 16)
+  const int dflt = kind == FNSM_OP_DIV ? 384 : 512;
+  const int threads = (cfg && cfg->threads != 0) ? cfg->threads : dflt;
   switch (threads) {
     case 128: return launch_tf32_nw<4>(kind, jac, op, rows, nrows, E, cfg, di, st);
     case 256: return launch_tf32_nw<8>(kind, jac, op, rows, nrows, E, cfg, di, st);
