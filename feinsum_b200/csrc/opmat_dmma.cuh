@@ -197,7 +197,10 @@ __device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps
   }
 }
 
-template <int NW>
+// STAGED: results leave through a shared-memory stage + one TMA store (4.4 KB per warp); otherwise
+// straight from the accumulator fragments with 8-byte streaming stores, which frees the shared
+// memory for two more warps (19 KB per warp staged -> 10 warps, 14.6 KB direct -> 12 warps)
+template <int NW, bool STAGED>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, const double* __restrict__ Dg,
            const double* __restrict__ ug, double* __restrict__ outg, long long E, int flags) {
@@ -207,7 +210,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   double* sL = sB + L::B_MAIN;
   double* slots = sB + L::B_DOUBLES;
   double* stages = slots + (size_t)NW * L::SLOT_DOUBLES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * OUT_BLOCK);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (STAGED ? (size_t)NW * OUT_BLOCK : 0));
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   // main operator fragments: sB[(kt*4 + nt)*32 + lane] = D[r][8nt+g][4jq+t]
@@ -232,7 +235,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   __syncthreads();
 
   double* s = slots + (size_t)warp * L::SLOT_DOUBLES;
-  double* stage = stages + (size_t)warp * OUT_BLOCK;
+  double* stage = stages + (size_t)warp * (STAGED ? OUT_BLOCK : 0);
   uint64_t* bar = &bars[warp];
   const double* sJ = s + 3 * L::U_SLAB;
   const long long nchunks = (E + kCH - 1) / kCH;
@@ -298,29 +301,47 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
         accL[kt & 1][m][2] = fma(a[m][kt], l2, accL[kt & 1][m][2]);
       }
     }
-    // ---- stage the [16][35] block, then one bulk store ----
     const long long e0 = cur * kCH;
-    if (lane == 0) tma_store_wait_read();          // previous block has left the stage
-    __syncwarp();
+    if (STAGED) {
+      // ---- stage the [16][35] block, then one bulk store ----
+      if (lane == 0) tma_store_wait_read();          // previous block has left the stage
+      __syncwarp();
 #pragma unroll
-    for (int m = 0; m < kME; ++m) {
-      double* o = stage + chunk_el(g, m) * 35;
-      const double l0 = quad_sum(accL[0][m][0] + accL[1][m][0]), l1 = quad_sum(accL[0][m][1] + accL[1][m][1]),
-                   l2 = quad_sum(accL[0][m][2] + accL[1][m][2]);
+      for (int m = 0; m < kME; ++m) {
+        double* o = stage + chunk_el(g, m) * 35;
+        const double l0 = quad_sum(accL[0][m][0] + accL[1][m][0]), l1 = quad_sum(accL[0][m][1] + accL[1][m][1]),
+                     l2 = quad_sum(accL[0][m][2] + accL[1][m][2]);
 #pragma unroll
-      for (int nt = 0; nt < kNT; ++nt) {
-        o[8 * nt + 2 * t] = acc[m][nt][0];
-        o[8 * nt + 2 * t + 1] = acc[m][nt][1];
+        for (int nt = 0; nt < kNT; ++nt) {
+          o[8 * nt + 2 * t] = acc[m][nt][0];
+          o[8 * nt + 2 * t + 1] = acc[m][nt][1];
+        }
+        if (t < kNL) o[32 + t] = t == 0 ? l0 : (t == 1 ? l1 : l2);
       }
-      if (t < kNL) o[32 + t] = t == 0 ? l0 : (t == 1 ? l1 : l2);
-    }
-    fence_proxy_async();
-    __syncwarp();
-    if (!dbg_nostore) {
-      if (tma) {
-        if (lane == 0) { tma_store_2d(&maps.out, stage, 0, (int)(cur * (kCH / 2))); tma_store_commit(); }
-      } else {
-        flush_plain(outg + e0 * 35, stage, e0, E, lane);
+      fence_proxy_async();
+      __syncwarp();
+      if (!dbg_nostore) {
+        if (tma) {
+          if (lane == 0) { tma_store_2d(&maps.out, stage, 0, (int)(cur * (kCH / 2))); tma_store_commit(); }
+        } else {
+          flush_plain(outg + e0 * 35, stage, e0, E, lane);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < kME; ++m) {
+        const long long e = e0 + chunk_el(g, m);
+        const double l0 = quad_sum(accL[0][m][0] + accL[1][m][0]), l1 = quad_sum(accL[0][m][1] + accL[1][m][1]),
+                     l2 = quad_sum(accL[0][m][2] + accL[1][m][2]);
+        if (e < E && !dbg_nostore) {
+          double* o = outg + e * 35;
+#pragma unroll
+          for (int nt = 0; nt < kNT; ++nt) {
+            stg_stream(o + 8 * nt + 2 * t, acc[m][nt][0]);
+            stg_stream(o + 8 * nt + 2 * t + 1, acc[m][nt][1]);
+          }
+          if (t < kNL) stg_stream(o + 32 + t, t == 0 ? l0 : (t == 1 ? l1 : l2));
+        }
       }
     }
     cur = nxt;
@@ -766,8 +787,14 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
     const bool is_div = kind == FNSM_OP_DIV;
     const size_t slot_d = is_div ? DivLayout::SLOT_DOUBLES : GradLayout::SLOT_DOUBLES;
     const size_t b_d = is_div ? DivLayout::B_DOUBLES : GradLayout::B_DOUBLES;
-    const size_t stage_d = is_div ? OUT_BLOCK : 3 * OUT_BLOCK;
-    const size_t smem = 8 * (b_d + (size_t)NW * (slot_d + stage_d)) + 8 * (size_t)NW + 8;
+    size_t stage_d = is_div ? OUT_BLOCK : 3 * OUT_BLOCK;
+    size_t smem = 8 * (b_d + (size_t)NW * (slot_d + stage_d)) + 8 * (size_t)NW + 8;
+    bool staged = true;
+    if (is_div && (smem > (size_t)di.max_smem_optin || (cfg && (cfg->reserved[0] & 8)))) {
+      staged = false;                                // no room for the output stage: direct stores
+      stage_d = 0;
+      smem = 8 * (b_d + (size_t)NW * slot_d) + 8 * (size_t)NW + 8;
+    }
     if (smem > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
     for (int r = 0; r < nrows; ++r) {
       const double* u = static_cast<const double*>(rows.field[r]);
@@ -778,8 +805,13 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
       else        ok = ok && map_rows(&maps.in, u, E, 35) && map_slabs(&maps.out, out, E, 35, 3);
       const int flags = (ok ? kFlagTma : 0) | (dbg & (kFlagNoLoad | kFlagNoStore));
       if (is_div) {
-        if (int rc = set_smem(k_div_dmma<NW>, smem)) return rc;
-        k_div_dmma<NW><<<grid_for_items(nchunks), threads, smem, st>>>(maps, J, O, u, out, E, flags);
+        if (staged) {
+          if (int rc = set_smem(k_div_dmma<NW, true>, smem)) return rc;
+          k_div_dmma<NW, true><<<grid_for_items(nchunks), threads, smem, st>>>(maps, J, O, u, out, E, flags);
+        } else {
+          if (int rc = set_smem(k_div_dmma<NW, false>, smem)) return rc;
+          k_div_dmma<NW, false><<<grid_for_items(nchunks), threads, smem, st>>>(maps, J, O, u, out, E, flags);
+        }
       } else {
         if (int rc = set_smem(k_grad_dmma<NW>, smem)) return rc;
         k_grad_dmma<NW><<<grid_for_items(nchunks), threads, smem, st>>>(maps, J, O, u, out, E, flags);
