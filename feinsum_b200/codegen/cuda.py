@@ -276,6 +276,7 @@ class CudaExecutor:
         self.lib = _cabi.lib()  # raises CudaBackendError when the .so is missing
         self.output_names = list(self.einsum.output_names)
         self._cfg = _cabi.make_cfg(dict(program.params))
+        self._prepared: dict[Any, Any] = {}
         row_dtypes = [
             np.result_type(*[a.dtype for a in row]) for row in self.einsum.args
         ]
@@ -339,12 +340,43 @@ class CudaExecutor:
     ) -> tuple[LaunchEvent, dict[str, Any]]:
         torch = _torch()
         q = self.cq if cq is None else as_queue(cq)
+        # Fast path for repeated calls with the same buffers (timing loops, time steppers): the
+        # checked and marshalled ABI call is remembered under the identity of every buffer passed.
+        try:
+            key = (q.stream, tuple((k, v.data_ptr(), v.dtype, tuple(v.shape), v.stride())
+                                   for k, v in arrays.items()))
+        except AttributeError:
+            key = None
+        hit = self._prepared.get(key) if key is not None else None
+        if hit is not None:
+            launch, outs = hit
+        else:
+            launch, outs, cacheable = self._prepare(q, arrays)
+            if cacheable and key is not None:
+                if len(self._prepared) >= 8:
+                    self._prepared.clear()
+                self._prepared[key] = (launch, outs)
+        if torch.cuda.current_device() == q.device.index:
+            launch()
+        else:
+            with torch.cuda.device(q.torch_device):
+                launch()
+        evt = torch.cuda.Event()
+        evt.record(q.torch_stream)
+        return LaunchEvent(evt), dict(outs)
+
+    def _prepare(self, q: CudaQueue, arrays: dict[str, Any]) -> tuple[Any, dict[str, Any], bool]:
+        """Validate *arrays*, allocate missing outputs, marshal the ABI call.  Returns the zero-argument
+        launcher, the outputs and whether the pair may be reused for identical arguments (only when
+        every output buffer was supplied by the caller)."""
+        torch = _torch()
         ins = {k: v for k, v in arrays.items() if k in self.einsum.all_args}
         for name, arr in ins.items():
             self._check_input(name, arr)
         sizes = self._bind_sizes(ins)
         out_shape = self._concrete(self.einsum.shape, sizes)
         outs: dict[str, Any] = {}
+        all_given = True
         for oname, odt in zip(self.output_names, self.out_dtypes):
             tdt = torch.float64 if odt == np.dtype("float64") else torch.float32
             if oname in arrays and arrays[oname] is not None:
@@ -353,23 +385,22 @@ class CudaExecutor:
                     raise ValueError(f"output '{oname}' has wrong shape/dtype/layout")
                 outs[oname] = o
             else:
+                all_given = False
                 outs[oname] = torch.empty(out_shape, dtype=tdt, device=q.torch_device)
         unknown = set(arrays) - set(self.einsum.all_args) - set(self.output_names)
         if unknown:
             raise TypeError(f"unexpected arguments: {sorted(unknown)}")
-
-        with torch.cuda.device(q.torch_device):
-            with torch.cuda.stream(q.torch_stream):
-                if all(o.numel() > 0 for o in outs.values()):
-                    self._launch(q, ins, outs, sizes)
-                evt = torch.cuda.Event()
-                evt.record(q.torch_stream)
-        return LaunchEvent(evt), outs
+        if all(o.numel() > 0 for o in outs.values()):
+            launch = self._launch(q, ins, outs, sizes)
+        else:
+            launch = lambda: None  # noqa: E731
+        return launch, outs, all_given
 
     # -- per-family launches ----------------------------------------------
     def _launch(
         self, q: CudaQueue, ins: dict[str, Any], outs: dict[str, Any], sizes: dict[str, int]
-    ) -> None:
+    ) -> Any:
+        """Marshal the C-ABI call(s) for these buffers; returns a zero-argument callable that issues them."""
         kid = self.plan.kernel_id
         stream = C.c_void_p(q.stream)
         es = self.einsum
@@ -386,33 +417,44 @@ class CudaExecutor:
             out_ptrs = (C.c_void_p * b)(*[outs[n].data_ptr() for n in self.output_names])
             E = sizes[es.index_to_dim_length[self.plan.long_index].name]  # type: ignore[union-attr]
             f = self.plan.facts
-            rc = self.lib.fnsm_b200_opmat_batch(
-                kind, _DTYPE_CODE[self.out_dtypes[0]],
-                C.c_void_p(jac.data_ptr()), C.c_void_p(op.data_ptr()),
-                fields, out_ptrs, b, f["n_outer"], f["n_i"], f["n_j"],
-                C.c_int64(E), self._cfg, stream,
-            )
-            _cabi.check(rc, f"fnsm_b200_opmat_batch[{kid}]")
-        elif kid == "tensor_product":
+            args = (kind, _DTYPE_CODE[self.out_dtypes[0]],
+                    C.c_void_p(jac.data_ptr()), C.c_void_p(op.data_ptr()),
+                    fields, out_ptrs, b, f["n_outer"], f["n_i"], f["n_j"],
+                    C.c_int64(E), self._cfg, stream)
+            fn = self.lib.fnsm_b200_opmat_batch
+
+            def launch() -> None:
+                rc = fn(*args)
+                if rc:
+                    _cabi.check(rc, f"fnsm_b200_opmat_batch[{kid}]")
+
+            return launch
+        if kid == "tensor_product":
             perm = self.plan.perm
             E = sizes[es.index_to_dim_length[self.plan.long_index].name]  # type: ignore[union-attr]
             f = self.plan.facts
+            calls = []
             for row, oname in zip(es.args, self.output_names):
                 A = ins[row[perm[0]].name]
                 M = ins[row[perm[1]].name]
-                rc = self.lib.fnsm_b200_tensor_product(
-                    _DTYPE_CODE[self.out_dtypes[0]],
-                    C.c_void_p(A.data_ptr()), C.c_void_p(M.data_ptr()),
-                    C.c_void_p(outs[oname].data_ptr()),
-                    f["n1d"], f["mode"], C.c_int64(E), self._cfg, stream,
-                )
-                _cabi.check(rc, "fnsm_b200_tensor_product")
-        else:
-            self._launch_generic(ins, outs, sizes, stream)
+                calls.append((_DTYPE_CODE[self.out_dtypes[0]],
+                              C.c_void_p(A.data_ptr()), C.c_void_p(M.data_ptr()),
+                              C.c_void_p(outs[oname].data_ptr()),
+                              f["n1d"], f["mode"], C.c_int64(E), self._cfg, stream))
+            fn = self.lib.fnsm_b200_tensor_product
+
+            def launch() -> None:
+                for a in calls:
+                    rc = fn(*a)
+                    if rc:
+                        _cabi.check(rc, "fnsm_b200_tensor_product")
+
+            return launch
+        return self._launch_generic(ins, outs, sizes, stream)
 
     def _launch_generic(
         self, ins: dict[str, Any], outs: dict[str, Any], sizes: dict[str, int], stream: Any
-    ) -> None:
+    ) -> Any:
         es = self.einsum
         free = list(es.out_idx_set)
         summed = list(es.sum_indices)
@@ -446,5 +488,11 @@ class CudaExecutor:
             *[ins[a.name].data_ptr() for row in es.args for a in row]
         )
         out_ptrs = (C.c_void_p * b)(*[outs[n].data_ptr() for n in self.output_names])
-        rc = self.lib.fnsm_b200_generic_einsum(C.byref(desc), b, in_ptrs, out_ptrs, stream)
-        _cabi.check(rc, "fnsm_b200_generic_einsum")
+        fn = self.lib.fnsm_b200_generic_einsum
+
+        def launch() -> None:
+            rc = fn(C.byref(desc), b, in_ptrs, out_ptrs, stream)
+            if rc:
+                _cabi.check(rc, "fnsm_b200_generic_einsum")
+
+        return launch

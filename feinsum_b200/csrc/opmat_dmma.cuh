@@ -213,19 +213,6 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (STAGED ? (size_t)NW * OUT_BLOCK : 0));
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  // main operator fragments: sB[(kt*4 + nt)*32 + lane] = D[r][8nt+g][4jq+t]
-  for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
-    const int ln = idx & 31, nt = (idx >> 5) % kNT, kt = (idx >> 5) / kNT;
-    const int g = ln >> 2, t = ln & 3, jq = kt / 3, r = kt - 3 * jq;
-    const int i = 8 * nt + g, j = 4 * jq + t;
-    sB[idx] = (j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
-  }
-  // left-over dofs: sL[(kt*4 + t)*4 + d] = D[r][32+d][4jq+t]
-  for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
-    const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
-    const int jq = kt / 3, r = kt - 3 * jq, j = 4 * jq + t;
-    sL[idx] = (d < kNL && j < 35) ? Dg[(r * 35 + 32 + d) * 35 + j] : 0.0;
-  }
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
     for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
@@ -245,6 +232,21 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   const bool tma = flags & kFlagTma, dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
   long long cur = wq.take(lane), nxt = wq.take(lane);
   if (cur < nchunks && !dbg_noload) div_issue(s, bar, &maps, Jg, ug, cur, E, tma, lane);
+  // operator tables are staged while the first TMA loads are in flight
+  // main operator fragments: sB[(kt*4 + nt)*32 + lane] = D[r][8nt+g][4jq+t]
+  for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
+    const int ln = idx & 31, nt = (idx >> 5) % kNT, kt = (idx >> 5) / kNT;
+    const int g = ln >> 2, t = ln & 3, jq = kt / 3, r = kt - 3 * jq;
+    const int i = 8 * nt + g, j = 4 * jq + t;
+    sB[idx] = (j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
+  }
+  // left-over dofs: sL[(kt*4 + t)*4 + d] = D[r][32+d][4jq+t]
+  for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
+    const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
+    const int jq = kt / 3, r = kt - 3 * jq, j = 4 * jq + t;
+    sL[idx] = (d < kNL && j < 35) ? Dg[(r * 35 + 32 + d) * 35 + j] : 0.0;
+  }
+  __syncthreads();
   for (uint32_t n = 0; cur < nchunks; ++n) {
     if (!dbg_noload) mbar_wait(bar, n & 1u);
     // ---- slot -> A fragments (Jacobian folded in) ----
@@ -446,13 +448,6 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * 3 * OUT_BLOCK);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  // sB[(tile*KT + kt)*32 + lane]: B[k = t][n = c], c = lane>>2 -> value v = 2*tile + (c&1) of lane c>>1
-  for (int idx = threadIdx.x; idx < L::B_DOUBLES; idx += blockDim.x) {
-    const int ln = idx & 31, kt = (idx >> 5) % L::KT, tile = (idx >> 5) / L::KT;
-    const int c = ln >> 2, t = ln & 3;
-    const int v = 2 * tile + (c & 1), i = 9 * (c >> 1) + v / 3, r = v % 3, j = 4 * kt + t;
-    sB[idx] = (v < 27 && i < 35 && j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
-  }
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
     for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
@@ -472,6 +467,15 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
   const bool tma = flags & kFlagTma, dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
   long long cur = wq.take(lane), nxt = wq.take(lane);
   if (cur < nchunks && !dbg_noload) grad_issue(s, bar, &maps, Jg, ug, cur, E, tma, lane);
+  // operator tables are staged while the first TMA loads are in flight
+  // sB[(tile*KT + kt)*32 + lane]: B[k = t][n = c], c = lane>>2 -> value v = 2*tile + (c&1) of lane c>>1
+  for (int idx = threadIdx.x; idx < L::B_DOUBLES; idx += blockDim.x) {
+    const int ln = idx & 31, kt = (idx >> 5) % L::KT, tile = (idx >> 5) / L::KT;
+    const int c = ln >> 2, t = ln & 3;
+    const int v = 2 * tile + (c & 1), i = 9 * (c >> 1) + v / 3, r = v % 3, j = 4 * kt + t;
+    sB[idx] = (v < 27 && i < 35 && j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
+  }
+  __syncthreads();
   for (uint32_t n = 0; cur < nchunks; ++n) {
     if (!dbg_noload) mbar_wait(bar, n & 1u);
     double a[kME][L::KT];
@@ -572,20 +576,6 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * OUT_BLOCK);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  // sB[(kt*4 + nt)*32 + lane] = Op(f, 8nt+g, j),  k = 4kt+t = 15 f + j
-  for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
-    const int ln = idx & 31, nt = (idx >> 5) % kNT, kt = (idx >> 5) / kNT;
-    const int g = ln >> 2, t = ln & 3, k = 4 * kt + t, f = k / 15, j = k - 15 * f;
-    const int i = 8 * nt + g;
-    sB[idx] = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
-  }
-  for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
-    const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
-    const int k = 4 * kt + t, f = k / 15, j = k - 15 * f, i = 32 + d;
-    double v = 0.0;
-    if (d < kNL) v = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
-    sL[idx] = v;
-  }
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
     for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
@@ -608,6 +598,22 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
   int fld = 0;
   if (cur < nchunks)
     lift_issue<FE>(s, bar, &maps.in[0], &maps.jac, Jg, static_cast<const double*>(rows.field[0]), cur, E, tma, lane);
+  // operator tables are staged while the first TMA loads are in flight
+  // sB[(kt*4 + nt)*32 + lane] = Op(f, 8nt+g, j),  k = 4kt+t = 15 f + j
+  for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
+    const int ln = idx & 31, nt = (idx >> 5) % kNT, kt = (idx >> 5) / kNT;
+    const int g = ln >> 2, t = ln & 3, k = 4 * kt + t, f = k / 15, j = k - 15 * f;
+    const int i = 8 * nt + g;
+    sB[idx] = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
+  }
+  for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
+    const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
+    const int k = 4 * kt + t, f = k / 15, j = k - 15 * f, i = 32 + d;
+    double v = 0.0;
+    if (d < kNL) v = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
+    sL[idx] = v;
+  }
+  __syncthreads();
   for (uint32_t n = 0; cur < nchunks; ++n) {
     mbar_wait(bar, n & 1u);
     double a[kME][L::KT];
@@ -711,10 +717,28 @@ inline bool dmma_supported(int kind, int n_outer, int ni, int nj) {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// opt in to > 48 KB of dynamic shared memory; remembered per (kernel address, device) so the steady-state
+// launch path makes no attribute call (the cap is only ever raised).  Keyed by the function ADDRESS: every
+// instantiation of one kernel template has the same pointer type, so a per-type static would be shared.
+struct SmemGrant { std::atomic<const void*> tag; std::atomic<size_t> bytes; };
 template <class K>
 static int set_smem(K kernel, size_t smem) {
+  constexpr int kSlots = 256;
+  static SmemGrant grants[kSlots];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const void* fn = reinterpret_cast<const void*>(kernel);
+  const uint64_t h = ((uint64_t)reinterpret_cast<uintptr_t>(fn) >> 4) * 0x9E3779B97F4A7C15ull + (uint64_t)dev * 0x632BE5ABull;
+  SmemGrant& g = grants[(h >> 32) % kSlots];
+  // the slot is tagged with fn + dev; a colliding kernel simply re-issues the attribute call
+  const void* tag = static_cast<const char*>(fn) + dev;
+  if (g.tag.load(std::memory_order_acquire) == tag && g.bytes.load(std::memory_order_relaxed) >= smem) return FNSM_OK;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  return e == cudaSuccess ? FNSM_OK : (int)e;
+  if (e != cudaSuccess) return (int)e;
+  g.tag.store(nullptr, std::memory_order_release);
+  g.bytes.store(smem, std::memory_order_relaxed);
+  g.tag.store(tag, std::memory_order_release);
+  return FNSM_OK;
 }
 
 // cuTensorMapEncodeTiled, fetched through the runtime (the library links cudart only)
@@ -734,14 +758,45 @@ static EncodeTiledFn tensor_map_encoder() {
   return fn;
 }
 // fp64 tensor map of rank 2 or 3; dims / box innermost first, strides (bytes) of dims 1..rank-1
-static bool make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
-                     const cuuint64_t* strides, const cuuint32_t* box) {
+// Encoding a descriptor costs ~1 us of host time and a launch needs 3-9 of them; timing loops and
+// time-stepping codes call with the same buffers over and over, so the last encodings are kept in a
+// small per-thread cache keyed by everything the encoder sees.
+struct MapKey {
+  const void* base; int dtype, rank; cuuint64_t dims[3], strides[2]; cuuint32_t box[3];
+  bool operator==(const MapKey& o) const {
+    if (base != o.base || dtype != o.dtype || rank != o.rank) return false;
+    for (int k = 0; k < rank; ++k) if (dims[k] != o.dims[k] || box[k] != o.box[k]) return false;
+    for (int k = 0; k + 1 < rank; ++k) if (strides[k] != o.strides[k]) return false;
+    return true;
+  }
+};
+static bool make_map_typed(CUtensorMap* tm, CUtensorMapDataType dtype, const void* base, int rank,
+                           const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
+  constexpr int N = 32;
+  thread_local MapKey keys[N];
+  thread_local CUtensorMap maps[N];
+  thread_local int used = 0, next = 0;
+  MapKey key{};
+  key.base = base; key.dtype = (int)dtype; key.rank = rank;
+  for (int k = 0; k < rank; ++k) { key.dims[k] = dims[k]; key.box[k] = box[k]; }
+  for (int k = 0; k + 1 < rank; ++k) key.strides[k] = strides[k];
+  for (int i = 0; i < used; ++i)
+    if (keys[i] == key) { *tm = maps[i]; return true; }
   EncodeTiledFn enc = tensor_map_encoder();
   if (!enc) return false;
   const cuuint32_t ones[3] = {1, 1, 1};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
-             ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  if (enc(tm, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, ones,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  keys[next] = key; maps[next] = *tm;
+  next = (next + 1) % N;
+  if (used < N) ++used;
+  return true;
+}
+static bool make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
+                     const cuuint64_t* strides, const cuuint32_t* box) {
+  return make_map_typed(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, base, rank, dims, strides, box);
 }
 // (E, W) row-major with W*2 doubles per element pair: box = 8 pairs = one 16-element chunk
 static bool map_rows(CUtensorMap* tm, const void* base, long long E, int W) {

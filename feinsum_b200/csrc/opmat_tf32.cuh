@@ -124,13 +124,6 @@ k_div_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, co
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  // fragment (kt, nt): lane (n = g, k = t / t + 4): D[r][8nt+g][j], 35 r + j = 8kt + t (+4)
-  fill_b_table(sB, L::KT * L::NT, [&](int frag, int ln, int half) {
-    const int kt = frag / L::NT, nt = frag - kt * L::NT;
-    const int g = ln >> 2, t = ln & 3, k = 8 * kt + t + 4 * half, i = 8 * nt + g;
-    const int r = k / 35, j = k - 35 * r;
-    return (k < 105 && i < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.f;
-  });
   if (threadIdx.x == 0) {
     for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
     *work_ctr = 0u;
@@ -149,6 +142,15 @@ k_div_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, co
 
   long long cur = wq.take(lane), nxt = wq.take(lane);
   if (cur < nchunks) div32_issue(s, bar, &maps, Jg, ug, cur, E, tma, lane);
+  // operator tables are staged while the first TMA loads are in flight
+  // fragment (kt, nt): lane (n = g, k = t / t + 4): D[r][8nt+g][j], 35 r + j = 8kt + t (+4)
+  fill_b_table(sB, L::KT * L::NT, [&](int frag, int ln, int half) {
+    const int kt = frag / L::NT, nt = frag - kt * L::NT;
+    const int g = ln >> 2, t = ln & 3, k = 8 * kt + t + 4 * half, i = 8 * nt + g;
+    const int r = k / 35, j = k - 35 * r;
+    return (k < 105 && i < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.f;
+  });
+  __syncthreads();
   for (uint32_t n = 0; cur < nchunks; ++n) {
     mbar_wait(bar, n & 1u);
     // ---- slot -> A fragments: rows g and g + 8 of the chunk, Jacobian folded in, split hi / lo ----
@@ -324,13 +326,6 @@ k_grad_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, c
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  // fragment (tile, kt): column c = g holds value v = 2 tile + (c & 1) of lane c >> 1: (dof 9 (c>>1) + v/3, r = v%3)
-  fill_b_table(sB, L::NTILE * L::KT, [&](int frag, int ln, int half) {
-    const int tile = frag / L::KT, kt = frag - tile * L::KT;
-    const int c = ln >> 2, t = ln & 3, j = 8 * kt + t + 4 * half;
-    const int v = 2 * tile + (c & 1), i = 9 * (c >> 1) + v / 3, r = v % 3;
-    return (v < 27 && i < 35 && j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.f;
-  });
   if (threadIdx.x == 0) {
     for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
     *work_ctr = 0u;
@@ -349,6 +344,15 @@ k_grad_tf32(const __grid_constant__ OpMaps maps, const float* __restrict__ Jg, c
 
   long long cur = wq.take(lane), nxt = wq.take(lane);
   if (cur < nchunks) grad32_issue(s, bar, &maps, Jg, ug, cur, E, tma, lane);
+  // operator tables are staged while the first TMA loads are in flight
+  // fragment (tile, kt): column c = g holds value v = 2 tile + (c & 1) of lane c >> 1: (dof 9 (c>>1) + v/3, r = v%3)
+  fill_b_table(sB, L::NTILE * L::KT, [&](int frag, int ln, int half) {
+    const int tile = frag / L::KT, kt = frag - tile * L::KT;
+    const int c = ln >> 2, t = ln & 3, j = 8 * kt + t + 4 * half;
+    const int v = 2 * tile + (c & 1), i = 9 * (c >> 1) + v / 3, r = v % 3;
+    return (v < 27 && i < 35 && j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.f;
+  });
+  __syncthreads();
   for (uint32_t n = 0; cur < nchunks; ++n) {
     mbar_wait(bar, n & 1u);
     uint32_t ahi[L::KT][4], alo[L::KT][4];
@@ -450,13 +454,6 @@ k_lift_tf32(const __grid_constant__ LiftMaps maps, const float* __restrict__ Jg,
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  fill_b_table(sB, L::KT * L::NT, [&](int frag, int ln, int half) {
-    const int kt = frag / L::NT, nt = frag - kt * L::NT;
-    const int g = ln >> 2, t = ln & 3, k = 8 * kt + t + 4 * half, i = 8 * nt + g;
-    const int f = k / 15, j = k - 15 * f;
-    if (k >= 60 || i >= 35) return 0.f;
-    return FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
-  });
   if (threadIdx.x == 0) {
     for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
     *work_ctr = 0u;
@@ -477,6 +474,15 @@ k_lift_tf32(const __grid_constant__ LiftMaps maps, const float* __restrict__ Jg,
   int fld = 0;
   if (cur < nchunks)
     lift32_issue<FE>(s, bar, &maps.in[0], &maps.jac, Jg, static_cast<const float*>(rows.field[0]), cur, E, tma, lane);
+  // operator tables are staged while the first TMA loads are in flight
+  fill_b_table(sB, L::KT * L::NT, [&](int frag, int ln, int half) {
+    const int kt = frag / L::NT, nt = frag - kt * L::NT;
+    const int g = ln >> 2, t = ln & 3, k = 8 * kt + t + 4 * half, i = 8 * nt + g;
+    const int f = k / 15, j = k - 15 * f;
+    if (k >= 60 || i >= 35) return 0.f;
+    return FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
+  });
+  __syncthreads();
   for (uint32_t n = 0; cur < nchunks; ++n) {
     mbar_wait(bar, n & 1u);
     uint32_t ahi[L::KT][4], alo[L::KT][4];
@@ -561,12 +567,7 @@ k_lift_tf32(const __grid_constant__ LiftMaps maps, const float* __restrict__ Jg,
 // ------------------------------------------------------------ launchers ----
 static bool make_map32(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
                        const cuuint64_t* strides, const cuuint32_t* box) {
-  EncodeTiledFn enc = tensor_map_encoder();
-  if (!enc) return false;
-  const cuuint32_t ones[3] = {1, 1, 1};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
-             ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return make_map_typed(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides, box);
 }
 // (E, W) fp32 rows viewed as (E/4, 4W): box = 4 quads = one 16-element chunk
 static bool map32_rows(CUtensorMap* tm, const void* base, long long E, int W) {
