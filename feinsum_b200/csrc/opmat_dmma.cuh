@@ -100,6 +100,16 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
+// 16-byte shared-memory load as a volatile asm statement: keeps its place among the (volatile) DMMAs
+__device__ __forceinline__ double2 lds_v2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+// c += a * b as a volatile asm statement (stays between the DMMAs it was written between)
+__device__ __forceinline__ void dfma_inplace(double& c, double a, double b) {
+  asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(c) : "d"(a), "d"(b));
+}
 __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 lanes sharing g
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -233,11 +243,12 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   long long cur = wq.take(lane), nxt = wq.take(lane);
   if (cur < nchunks && !dbg_noload) div_issue(s, bar, &maps, Jg, ug, cur, E, tma, lane);
   // operator tables are staged while the first TMA loads are in flight
-  // main operator fragments: sB[(kt*4 + nt)*32 + lane] = D[r][8nt+g][4jq+t]
+  // main operator fragments, column tiles in pairs so that one LDS.128 feeds two of them:
+  // sB[((kt*2 + p)*32 + lane)*2 + h] = D[r][8(2p+h)+g][4jq+t]
   for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
-    const int ln = idx & 31, nt = (idx >> 5) % kNT, kt = (idx >> 5) / kNT;
+    const int h = idx & 1, ln = (idx >> 1) & 31, p = (idx >> 6) & 1, kt = idx >> 7;
     const int g = ln >> 2, t = ln & 3, jq = kt / 3, r = kt - 3 * jq;
-    const int i = 8 * nt + g, j = 4 * jq + t;
+    const int i = 8 * (2 * p + h) + g, j = 4 * jq + t;
     sB[idx] = (j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
   }
   // left-over dofs: sL[(kt*4 + t)*4 + d] = D[r][32+d][4jq+t]
@@ -277,30 +288,39 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
 
     // ---- DMMA stream ----
     double acc[kME][kNT][2];
-    double accL[2][kME][kNL];      // two partial sums per value: DFMA latency >> 6 chains
+    double accL[1][kME][kNL];      // one chain per value: consecutive links are a whole k-tile (8 DMMAs) apart
 #pragma unroll
     for (int m = 0; m < kME; ++m) {
 #pragma unroll
       for (int nt = 0; nt < kNT; ++nt) { acc[m][nt][0] = 0.0; acc[m][nt][1] = 0.0; }
 #pragma unroll
-      for (int d = 0; d < kNL; ++d) { accL[0][m][d] = 0.0; accL[1][m][d] = 0.0; }
+      for (int d = 0; d < kNL; ++d) accL[0][m][d] = 0.0;
     }
+    // B fragments are fetched one k-tile ahead of their DMMAs (ptxas otherwise funnels every fragment
+    // through one register pair and exposes the LDS latency to each pair of DMMAs)
+    const uint32_t bB = smem_u32(sB) + lane * 16, bL = smem_u32(sL) + t * 32;
+    double2 bq[2][2], lq[2][2];
+    bq[0][0] = lds_v2(bB); bq[0][1] = lds_v2(bB + 512);
+    lq[0][0] = lds_v2(bL); lq[0][1] = lds_v2(bL + 16);
 #pragma unroll
     for (int kt = 0; kt < L::KT; ++kt) {
-      const double* bp = sB + (kt * kNT) * 32 + lane;
-#pragma unroll
-      for (int nt = 0; nt < kNT; ++nt) {
-        const double b = bp[nt * 32];
-#pragma unroll
-        for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m][kt], b);
+      const int c = kt & 1, nx = c ^ 1;
+      if (kt + 1 < L::KT) {
+        bq[nx][0] = lds_v2(bB + (kt + 1) * 1024); bq[nx][1] = lds_v2(bB + (kt + 1) * 1024 + 512);
+        lq[nx][0] = lds_v2(bL + (kt + 1) * 128);  lq[nx][1] = lds_v2(bL + (kt + 1) * 128 + 16);
       }
-      const double2 l01 = *reinterpret_cast<const double2*>(sL + (kt * 4 + t) * 4);
-      const double l2 = sL[(kt * 4 + t) * 4 + 2];
 #pragma unroll
       for (int m = 0; m < kME; ++m) {
-        accL[kt & 1][m][0] = fma(a[m][kt], l01.x, accL[kt & 1][m][0]);
-        accL[kt & 1][m][1] = fma(a[m][kt], l01.y, accL[kt & 1][m][1]);
-        accL[kt & 1][m][2] = fma(a[m][kt], l2, accL[kt & 1][m][2]);
+        dmma884(acc[m][0], a[m][kt], bq[c][0].x);
+        dmma884(acc[m][1], a[m][kt], bq[c][0].y);
+        dmma884(acc[m][2], a[m][kt], bq[c][1].x);
+        dmma884(acc[m][3], a[m][kt], bq[c][1].y);
+      }
+#pragma unroll
+      for (int m = 0; m < kME; ++m) {
+        dfma_inplace(accL[0][m][0], a[m][kt], lq[c][0].x);
+        dfma_inplace(accL[0][m][1], a[m][kt], lq[c][0].y);
+        dfma_inplace(accL[0][m][2], a[m][kt], lq[c][1].x);
       }
     }
     const long long e0 = cur * kCH;
@@ -311,8 +331,8 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
 #pragma unroll
       for (int m = 0; m < kME; ++m) {
         double* o = stage + chunk_el(g, m) * 35;
-        const double l0 = quad_sum(accL[0][m][0] + accL[1][m][0]), l1 = quad_sum(accL[0][m][1] + accL[1][m][1]),
-                     l2 = quad_sum(accL[0][m][2] + accL[1][m][2]);
+        const double l0 = quad_sum(accL[0][m][0]), l1 = quad_sum(accL[0][m][1]),
+                     l2 = quad_sum(accL[0][m][2]);
 #pragma unroll
         for (int nt = 0; nt < kNT; ++nt) {
           o[8 * nt + 2 * t] = acc[m][nt][0];
@@ -333,8 +353,8 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
 #pragma unroll
       for (int m = 0; m < kME; ++m) {
         const long long e = e0 + chunk_el(g, m);
-        const double l0 = quad_sum(accL[0][m][0] + accL[1][m][0]), l1 = quad_sum(accL[0][m][1] + accL[1][m][1]),
-                     l2 = quad_sum(accL[0][m][2] + accL[1][m][2]);
+        const double l0 = quad_sum(accL[0][m][0]), l1 = quad_sum(accL[0][m][1]),
+                     l2 = quad_sum(accL[0][m][2]);
         if (e < E && !dbg_nostore) {
           double* o = outg + e * 35;
 #pragma unroll
