@@ -9,6 +9,7 @@
 #include "opmat_simt.cuh"
 #include "opmat_dmma.cuh"
 #include "opmat_tf32.cuh"
+#include "opmat_tc32.cuh"
 #include <cstdio>
 #include <cstring>
 
@@ -24,7 +25,8 @@ int opmat_cfg_space(int kernel_id, fnsm_cfg_range* out, int cap) {
   (void)kernel_id;
   fnsm_cfg_range tmp[5];
   int n = 0;
-  set_range(&tmp[n++], "variant", 0, 2, 1, 0);        // 0 = auto, 1 = tensor path (DMMA / 3xTF32, p=4 shapes), 2 = simt
+  // 0 = auto, 1 = mma.sync tensor path (DMMA / 3xTF32, p=4 shapes), 2 = simt, 3 = tcgen05 3xTF32 (fp32, p=4 shapes)
+  set_range(&tmp[n++], "variant", 0, 3, 1, 0);
   set_range(&tmp[n++], "tile_e", 8, 64, 8, 16);        // simt: elements per CTA tile
   set_range(&tmp[n++], "ctas_per_sm", 1, 8, 1, 0);     // persistent grid size
   set_range(&tmp[n++], "threads", 128, 448, 32, 0);   // dmma: 32 * warps per persistent CTA (4, 8..12, 14)
@@ -79,11 +81,15 @@ static int opmat_dispatch(int kind, int dtype, const void* jac, const void* op,
   DevInfo di;
   if (int rc = device_info(&di)) return rc;
   int variant = cfg ? cfg->variant : 0;    // 0: library default
-  if (variant < 0 || variant > 2) return FNSM_E_BAD_CONFIG;
-  // variant 1 = tensor path: fp64 DMMA, fp32 3xTF32 -- compiled for the p = 4 tet shapes
+  if (variant < 0 || variant > 3) return FNSM_E_BAD_CONFIG;
+  // variant 1 = mma.sync tensor path: fp64 DMMA, fp32 3xTF32; variant 3 = tcgen05 3xTF32 (fp32 only) --
+  // both compiled for the p = 4 tet shapes.  auto: fp64 -> 1; fp32 -> 3 when the operands qualify for
+  // its TMA tensor maps (E % 4 == 0, 16-byte aligned bases), else 1; other shapes -> 2.
   const bool tensor_ok = dmma_supported(kind, n_outer, ni, nj);
-  if (variant == 1 && !tensor_ok) return FNSM_E_UNSUPPORTED;
-  if (variant == 0) variant = tensor_ok ? 1 : 2;
+  if ((variant == 1 || variant == 3) && !tensor_ok) return FNSM_E_UNSUPPORTED;
+  if (variant == 3 && dtype != FNSM_F32) return FNSM_E_UNSUPPORTED;
+  const bool is_auto = variant == 0;
+  if (is_auto) variant = tensor_ok ? (dtype == FNSM_F32 ? 3 : 1) : 2;
   for (int r0 = 0; r0 < b; r0 += 8) {
     const int nr = (b - r0 < 8) ? (b - r0) : 8;
     OpmatRows rows{};
@@ -95,7 +101,10 @@ static int opmat_dispatch(int kind, int dtype, const void* jac, const void* op,
     int rc;
     if (variant == 1 && dtype == FNSM_F64)
       rc = launch_dmma(kind, jac, op, rows, nr, n_outer, ni, nj, E, cfg, di, st);
-    else if (variant == 1)
+    else if (variant == 3) {
+      rc = launch_tc32(kind, jac, op, rows, nr, E, di, st);
+      if (rc == FNSM_E_ALIGNMENT && is_auto) rc = launch_tf32(kind, jac, op, rows, nr, E, cfg, di, st);
+    } else if (variant == 1)
       rc = launch_tf32(kind, jac, op, rows, nr, E, cfg, di, st);
     else if (dtype == FNSM_F64)
       rc = launch_simt<double>(kind, jac, op, rows, nr, n_outer, ni, nj, E, cfg, di, st);

@@ -1,0 +1,712 @@
+// fp32 DG operator kernels on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators
+// in TMEM), 3xTF32: both operands are split hi = tf32(x), lo = tf32(x - hi) and
+//     main  = A_hi B_hi            (its own fp32 accumulator)
+//     corr  = A_hi B_lo + A_lo B_hi (a second accumulator; the lo*lo term is dropped)
+// restores ~2^-21 relative accuracy per product (opmat_tf32.cuh, the mma.sync variant, explains why
+// the cross terms get their own accumulator).  The legacy mma.sync path tops out at 277 TFLOP/s TF32
+// (tools/ubench4) -> its 3xTF32 kernels are capped at ~89 % of the fp32 roofline by the tensor pipe
+// alone; tcgen05 lifts that cap, the kernels below are bounded by HBM.
+//
+// Shape of one tile: M = 128 elements (TMEM lane = element), K = contracted dofs, N = output columns.
+//   grad:  C[e][(i,r)] = sum_j u[e,j] D[r,i,j]   K = 35 -> 40, N = 105 -> 112, column n = 3 i + r;
+//          out[x,e,i] = sum_r J[x,r,e] C[e][(i,r)] is applied by the thread that owns element e
+//          (tcgen05.ld 32x32b: one TMEM lane per thread) -- no shuffles, no shared-memory transpose.
+//   One MMA per k-step computes  A_hi x [B_hi | pad | B_lo]  (N = 240: columns 0..111 main,
+//   128..239 corr), a second one (N = 112) adds  A_lo x B_hi  into the corr columns.
+//
+// Structure: one persistent CTA per SM with two independent GROUPS of 4 warps.  A group owns two TMA
+// slots (double buffered element rows), an A_hi/A_lo operand buffer that doubles as the output
+// stage, 224 TMEM columns, and walks its tiles serially:
+//     wait slot -> split rows into the UMMA canonical K-major layout (no swizzle) -> elected thread
+//     issues the MMAs + tcgen05.commit and re-arms the slot with the TMA load two tiles ahead ->
+//     wait commit -> tcgen05.ld, apply J, stage -> one TMA tensor store.
+// While one group waits on its MMAs / stores the other converts or drains, so the SM stays busy
+// without any cross-group synchronisation.
+#pragma once
+#include "opmat_tf32.cuh"
+
+namespace fnsm {
+
+// ------------------------------------------------------------- tcgen05 -----
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+               :: "r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B stored as 128
+// contiguous bytes; LBO = byte distance between the two core matrices of one k-step (K direction),
+// SBO = byte distance between consecutive 8-row groups (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, TF32 x TF32, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: A lives in TMEM (lane = row, one fp32 column per k); issued by ONE thread
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                  "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// arrive on an mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               :: "r"(smem_u32(bar)) : "memory");
+}
+// 8 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void group_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
+// ================================================================ GRAD =====
+struct GradTC {
+  static constexpr int TM = 128;                        // elements per tile
+  static constexpr int K = 40, KS = 5;                  // padded contraction length, k-steps of 8
+  static constexpr int N = 112;                         // columns n = 3 i + r (105 used)
+  static constexpr int NP = 128;                        // column pitch main -> corr (TMEM) = row pitch hi -> lo (table)
+  static constexpr int NB = NP + N;                     // rows of the operator table: [hi | pad | lo] = 240
+  static constexpr int GROUPS = 2, THREADS = GROUPS * 128;
+  static constexpr int B_LBO = NB * 16;                 // operator table: addr(n, k) = (k/4) B_LBO + 16 n + 4 (k%4)
+  static constexpr int A_LBO = TM * 16;                 // A operand:      addr(e, k) = (k/4) A_LBO + 16 e + 4 (k%4)
+  static constexpr int B_BYTES = (K / 4) * B_LBO;       // 35 840
+  static constexpr int A_BYTES = (K / 4) * A_LBO;       // 20 480 per half (hi, lo)
+  static constexpr int SLOT_BYTES = TM * 35 * 4;        // 17 920: u rows of one tile
+  static constexpr int STAGE_BYTES = 3 * TM * 35 * 4;   // 53 760: out[x][e][i]; the A operand aliases it
+  static constexpr int GROUP_BYTES = 2 * SLOT_BYTES + STAGE_BYTES;
+  static constexpr int TMEM_COLS_PER_GROUP = 256;       // 240 used
+  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 128;
+  static_assert(2 * A_BYTES <= STAGE_BYTES, "A operand must fit into the output stage");
+};
+
+struct GradTCMaps { CUtensorMap in, out; };
+
+__global__ void __launch_bounds__(GradTC::THREADS, 1)
+k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ Jg, const float* __restrict__ Dg,
+            long long E) {
+  using L = GradTC;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* sB = smem_raw;
+  unsigned char* groups = smem_raw + L::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(groups + (size_t)L::GROUPS * L::GROUP_BYTES);   // [group][full0, full1, mma]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * L::GROUPS);
+
+  const int warp = uniform_warp_idx();
+  const int gq = warp >> 2;                              // group
+  const int row = threadIdx.x & 127;                     // element row of the tile = TMEM lane
+  const bool leader = row == 0;
+
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 3 * L::GROUPS; ++k) mbar_init(&bars[k], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  // operator table [hi | pad | lo], UMMA K-major canonical layout, zero padded (k >= 35, n >= 105)
+  for (int idx = threadIdx.x; idx < L::NP * L::K; idx += blockDim.x) {
+    const int n = idx / L::K, k = idx - n * L::K;
+    const int i = n / 3, r = n - 3 * i;
+    const float v = (n < 105 && k < 35) ? Dg[(r * 35 + i) * 35 + k] : 0.f;
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    const int off = (k >> 2) * L::B_LBO + (k & 3) * 4;
+    *reinterpret_cast<uint32_t*>(sB + off + n * 16) = hi;
+    if (n < L::N) *reinterpret_cast<uint32_t*>(sB + off + (L::NP + n) * 16) = lo;
+  }
+  fence_proxy_async();                                   // table is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot + (uint32_t)gq * L::TMEM_COLS_PER_GROUP;
+  const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp & 3) * 32u << 16);
+
+  unsigned char* gbase = groups + (size_t)gq * L::GROUP_BYTES;
+  float* slot[2] = {reinterpret_cast<float*>(gbase), reinterpret_cast<float*>(gbase + L::SLOT_BYTES)};
+  unsigned char* stage_b = gbase + 2 * L::SLOT_BYTES;
+  float* stage = reinterpret_cast<float*>(stage_b);
+  uint64_t* full = &bars[3 * gq];
+  uint64_t* mma_done = &bars[3 * gq + 2];
+  const int bar_id = 1 + gq;
+
+  const long long ntiles = (E + L::TM - 1) / L::TM;
+  const long long tile0 = (long long)blockIdx.x * L::GROUPS + gq, tstride = (long long)gridDim.x * L::GROUPS;
+  constexpr uint32_t idesc_wide = umma_idesc_tf32(L::TM, L::NB), idesc_half = umma_idesc_tf32(L::TM, L::N);
+
+  if (leader) {
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const long long tl = tile0 + p * tstride;
+      if (tl < ntiles) {
+        mbar_arrive_expect_tx(&full[p], L::SLOT_BYTES);
+        tma_load_2d(slot[p], &maps.in, 0, (int)(tl * (L::TM / 4)), &full[p]);
+      }
+    }
+  }
+  // Jacobian of this thread's element, fetched one tile ahead (coalesced: J[xr][e])
+  float Jn[9];
+  {
+    const long long e = tile0 * L::TM + row;
+#pragma unroll
+    for (int xr = 0; xr < 9; ++xr) Jn[xr] = (tile0 < ntiles && e < E) ? __ldg(Jg + (long long)xr * E + e) : 0.f;
+  }
+
+  uint32_t it = 0;
+  for (long long tile = tile0; tile < ntiles; tile += tstride, ++it) {
+    const int s = it & 1;
+    float Jr[9];
+#pragma unroll
+    for (int xr = 0; xr < 9; ++xr) Jr[xr] = Jn[xr];
+    {
+      const long long tn = tile + tstride, e = tn * L::TM + row;
+#pragma unroll
+      for (int xr = 0; xr < 9; ++xr) Jn[xr] = (tn < ntiles && e < E) ? __ldg(Jg + (long long)xr * E + e) : 0.f;
+    }
+    mbar_wait(&full[s], (it >> 1) & 1u);
+    // the A operand aliases the output stage: the previous tile's bulk store must have read it out
+    if (leader) tma_store_wait_read();
+    group_barrier(bar_id, 128);
+    // ---- element row -> A_hi / A_lo (K-major canonical layout: 16-byte k-quads, rows 16 B apart) ----
+    {
+      const float* su = slot[s] + row * 35;
+      unsigned char* ahi = stage_b + row * 16;
+      unsigned char* alo = ahi + L::A_BYTES;
+#pragma unroll
+      for (int kq = 0; kq < L::K / 4; ++kq) {
+        uint4 h, l;
+        split_tf32(4 * kq + 0 < 35 ? su[4 * kq + 0] : 0.f, h.x, l.x);
+        split_tf32(4 * kq + 1 < 35 ? su[4 * kq + 1] : 0.f, h.y, l.y);
+        split_tf32(4 * kq + 2 < 35 ? su[4 * kq + 2] : 0.f, h.z, l.z);
+        split_tf32(4 * kq + 3 < 35 ? su[4 * kq + 3] : 0.f, h.w, l.w);
+        *reinterpret_cast<uint4*>(ahi + kq * L::A_LBO) = h;
+        *reinterpret_cast<uint4*>(alo + kq * L::A_LBO) = l;
+      }
+    }
+    fence_proxy_async();                                 // generic-proxy writes -> tensor core / TMA reads
+    tc_fence_before();
+    group_barrier(bar_id, 128);
+    if (leader) {
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(stage_b), a_lo = a_hi + L::A_BYTES, b0 = smem_u32(sB);
+#pragma unroll
+      for (int ks = 0; ks < L::KS; ++ks) {
+        const uint64_t dah = umma_desc(a_hi + ks * 2 * L::A_LBO, L::A_LBO, 128);
+        const uint64_t dal = umma_desc(a_lo + ks * 2 * L::A_LBO, L::A_LBO, 128);
+        const uint64_t db = umma_desc(b0 + ks * 2 * L::B_LBO, L::B_LBO, 128);
+        umma_tf32(tmem_base, dah, db, idesc_wide, ks > 0);            // main | corr  (+)= A_hi [B_hi | B_lo]
+        umma_tf32(tmem_base + L::NP, dal, db, idesc_half, true);      // corr += A_lo B_hi
+      }
+      umma_commit(mma_done);
+      // the slot has been consumed by every thread of the group: fetch the tile two steps ahead
+      const long long tl = tile + 2 * tstride;
+      if (tl < ntiles) {
+        mbar_arrive_expect_tx(&full[s], L::SLOT_BYTES);
+        tma_load_2d(slot[s], &maps.in, 0, (int)(tl * (L::TM / 4)), &full[s]);
+      }
+    }
+    mbar_wait(mma_done, it & 1u);
+    tc_fence_after();
+    // ---- TMEM -> registers (8 dofs = 24 columns at a time), J applied, staged as out[x][e][i] ----
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      float m[24], c[24];
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        tmem_ld8(tmem_lane + 24 * q + 8 * p, reinterpret_cast<float(&)[8]>(m[8 * p]));
+        tmem_ld8(tmem_lane + L::NP + 24 * q + 8 * p, reinterpret_cast<float(&)[8]>(c[8 * p]));
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        const int i = 8 * q + d;
+        if (i < 35) {
+          const float T0 = m[3 * d] + c[3 * d], T1 = m[3 * d + 1] + c[3 * d + 1], T2 = m[3 * d + 2] + c[3 * d + 2];
+#pragma unroll
+          for (int x = 0; x < 3; ++x)
+            stage[(x * L::TM + row) * 35 + i] = fmaf(Jr[3 * x + 2], T2, fmaf(Jr[3 * x + 1], T1, Jr[3 * x] * T0));
+        }
+      }
+    }
+    tc_fence_before();                                   // TMEM reads done before the next tile's MMAs
+    fence_proxy_async();
+    group_barrier(bar_id, 128);
+    if (leader) {
+      tma_store_3d(&maps.out, stage, 0, (int)(tile * (L::TM / 4)), 0);
+      tma_store_commit();
+    }
+  }
+  if (leader) tma_store_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*tmem_slot, 512);
+}
+
+// ================================================================ LIFT =====
+// out_k[e,i] = sum_{f,j} Op(f,i,j) Jf(e,f) v_k[f,e,j]:  K = (f, j) = 60 -> 64, N = 35 -> 48.
+// The A operand (Jf v, split hi / lo) is written straight into TMEM by the thread that owns the row
+// (tcgen05.st) and consumed from there (tcgen05.mma with A in TMEM): no shared-memory round trip.
+// TMEM columns of a group: [0,48) main, [64,112) corr, [128,192) A_hi, [192,256) A_lo.
+// Work item = (tile, field); the face Jacobian of a tile is fetched once for its fields.
+struct LiftTC {
+  static constexpr int TM = 128;
+  static constexpr int K = 64, KS = 8;
+  static constexpr int N = 48, NP = 64, NB = NP + N;    // operator table rows [hi | pad | lo] = 112
+  static constexpr int GROUPS = 2, THREADS = GROUPS * 128;
+  static constexpr int B_LBO = NB * 16;
+  static constexpr int B_BYTES = (K / 4) * B_LBO;       // 28 672
+  static constexpr int V_SLAB = TM * 15;                // floats per face
+  static constexpr int SLOT_BYTES = 4 * V_SLAB * 4;     // 30 720
+  static constexpr int STAGE_BYTES = TM * 35 * 4;       // 17 920
+  static constexpr int GROUP_BYTES = 2 * SLOT_BYTES + STAGE_BYTES;
+  static constexpr int TMEM_COLS_PER_GROUP = 256, A_HI_COL = 128, A_LO_COL = 192;
+  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 128;
+};
+
+struct LiftTCMaps { CUtensorMap in[8]; CUtensorMap out[8]; };
+
+template <bool FE>
+__global__ void __launch_bounds__(LiftTC::THREADS, 1)
+k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ Jg, const float* __restrict__ Og,
+            int nrows, long long E) {
+  using L = LiftTC;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* sB = smem_raw;
+  unsigned char* groups = smem_raw + L::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(groups + (size_t)L::GROUPS * L::GROUP_BYTES);   // [group][full0, full1, mma]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * L::GROUPS);
+
+  const int warp = uniform_warp_idx();
+  const int gq = warp >> 2;
+  const int row = threadIdx.x & 127;
+  const bool leader = row == 0;
+
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 3 * L::GROUPS; ++k) mbar_init(&bars[k], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  // operator table [hi | pad | lo]: row n = dof i, k = 15 f + j
+  for (int idx = threadIdx.x; idx < L::NP * L::K; idx += blockDim.x) {
+    const int n = idx / L::K, k = idx - n * L::K;
+    const int f = k / 15, j = k - 15 * f;
+    float v = 0.f;
+    if (n < 35 && k < 60) v = FE ? Og[(n * 4 + f) * 15 + j] : Og[(f * 35 + n) * 15 + j];
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    const int off = (k >> 2) * L::B_LBO + (k & 3) * 4;
+    *reinterpret_cast<uint32_t*>(sB + off + n * 16) = hi;
+    if (n < L::N) *reinterpret_cast<uint32_t*>(sB + off + (L::NP + n) * 16) = lo;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot + (uint32_t)gq * L::TMEM_COLS_PER_GROUP;
+  const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp & 3) * 32u << 16);
+
+  unsigned char* gbase = groups + (size_t)gq * L::GROUP_BYTES;
+  float* slot[2] = {reinterpret_cast<float*>(gbase), reinterpret_cast<float*>(gbase + L::SLOT_BYTES)};
+  float* stage = reinterpret_cast<float*>(gbase + 2 * L::SLOT_BYTES);
+  uint64_t* full = &bars[3 * gq];
+  uint64_t* mma_done = &bars[3 * gq + 2];
+  const int bar_id = 1 + gq;
+
+  const long long ntiles = (E + L::TM - 1) / L::TM;
+  const long long tile0 = (long long)blockIdx.x * L::GROUPS + gq, tstride = (long long)gridDim.x * L::GROUPS;
+  constexpr uint32_t idesc_wide = umma_idesc_tf32(L::TM, L::NB), idesc_half = umma_idesc_tf32(L::TM, L::N);
+  // items of this group: (tile0, 0), (tile0, 1), ..., (tile0 + tstride, 0), ...; item index `it`
+  const long long my_tiles = tile0 < ntiles ? (ntiles - tile0 + tstride - 1) / tstride : 0;
+  const long long nitems = my_tiles * nrows;
+
+  auto issue = [&](long long item, int s) {             // leader only
+    const long long tl = tile0 + (item / nrows) * tstride;
+    const int fld = (int)(item % nrows);
+    mbar_arrive_expect_tx(&full[s], L::SLOT_BYTES);
+    tma_load_3d(slot[s], &maps.in[fld], 0, (int)(tl * (L::TM / 4)), 0, &full[s]);
+  };
+  if (leader) {
+    if (nitems > 0) issue(0, 0);
+    if (nitems > 1) issue(1, 1);
+  }
+  auto load_j = [&](long long tl, float (&J)[4]) {
+    const long long e = tl * L::TM + row;
+    if (tl < ntiles && e < E) {
+      if (FE) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) J[f] = __ldg(Jg + (long long)f * E + e);
+      } else {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(Jg) + e);
+        J[0] = v.x; J[1] = v.y; J[2] = v.z; J[3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int f = 0; f < 4; ++f) J[f] = 0.f;
+    }
+  };
+  float Jf[4], Jn[4];
+  load_j(tile0, Jn);
+
+  int fld = 0;
+  long long tile = tile0;
+  for (long long it = 0; it < nitems; ++it) {
+    const int s = (int)(it & 1);
+    if (fld == 0) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f) Jf[f] = Jn[f];
+      load_j(tile + tstride, Jn);
+    }
+    mbar_wait(&full[s], (uint32_t)(it >> 1) & 1u);
+    // ---- row of the slot -> A_hi / A_lo in TMEM ----
+    {
+      const float* sv = slot[s] + row * 15;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {                      // 16 k at a time
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int k = 16 * c + q, f = k / 15, j = k - 15 * f;
+          const float a = k < 60 ? Jf[f < 4 ? f : 3] * sv[(f < 4 ? f : 3) * L::V_SLAB + j] : 0.f;
+          split_tf32(a, hi[q], lo[q]);
+        }
+        tmem_st16(tmem_lane + L::A_HI_COL + 16 * c, hi);
+        tmem_st16(tmem_lane + L::A_LO_COL + 16 * c, lo);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    group_barrier(bar_id, 128);
+    if (leader) {
+      tc_fence_after();
+      const uint32_t b0 = smem_u32(sB);
+#pragma unroll
+      for (int ks = 0; ks < L::KS; ++ks) {
+        const uint64_t db = umma_desc(b0 + ks * 2 * L::B_LBO, L::B_LBO, 128);
+        umma_tf32_ts(tmem_base, tmem_base + L::A_HI_COL + 8 * ks, db, idesc_wide, ks > 0);
+        umma_tf32_ts(tmem_base + L::NP, tmem_base + L::A_LO_COL + 8 * ks, db, idesc_half, true);
+      }
+      umma_commit(mma_done);
+      if (it + 2 < nitems) { fence_proxy_async(); issue(it + 2, s); }
+      tma_store_wait_read();                             // the stage is free again (previous item's store)
+    }
+    mbar_wait(mma_done, (uint32_t)it & 1u);
+    tc_fence_after();
+    group_barrier(bar_id, 128);                          // ... and every thread knows it
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      float m[8], c[8];
+      tmem_ld8(tmem_lane + 8 * q, m);
+      tmem_ld8(tmem_lane + L::NP + 8 * q, c);
+      tmem_ld_wait();
+#pragma unroll
+      for (int d = 0; d < 8; ++d)
+        if (8 * q + d < 35) stage[row * 35 + 8 * q + d] = m[d] + c[d];
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    group_barrier(bar_id, 128);
+    if (leader) {
+      tma_store_2d(&maps.out[fld], stage, 0, (int)(tile * (L::TM / 4)));
+      tma_store_commit();
+    }
+    if (++fld == nrows) { fld = 0; tile += tstride; }
+  }
+  if (leader) tma_store_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*tmem_slot, 512);
+}
+
+// ================================================================= DIV =====
+// out[e,i] = sum_{r,j} D[r,i,j] w[r,e,j],  w[r,e,j] = sum_x J[x,r,e] u[x,e,j]:  N = 35 -> 48, K in three
+// chunks (one per r) of 35 -> 40.  The thread that owns element e folds the Jacobian, splits w and
+// writes chunk r into one of two A buffers in TMEM; the elected thread issues that chunk's MMAs while
+// the group folds the next chunk.  TMEM columns of a group: [0,48) main, [48,96) corr,
+// A buffer b: hi [96 + 80 b, +40), lo [136 + 80 b, +40).
+struct DivTC {
+  static constexpr int TM = 128;
+  static constexpr int KC = 40, KS_C = 5, NCHUNK = 3;   // per chunk: padded length, k-steps
+  static constexpr int N = 48, NB = 2 * N;              // operator table rows [hi | lo] = 96
+  static constexpr int GROUPS = 2, THREADS = GROUPS * 128;
+  static constexpr int B_LBO = NB * 16;                 // 1536
+  static constexpr int B_BYTES = NCHUNK * (KC / 4) * B_LBO;   // 46 080
+  static constexpr int U_SLAB = TM * 35;                // floats per x
+  static constexpr int SLOT_BYTES = 3 * U_SLAB * 4;     // 53 760
+  static constexpr int STAGE_BYTES = TM * 35 * 4;       // 17 920
+  static constexpr int GROUP_BYTES = SLOT_BYTES + STAGE_BYTES;
+  static constexpr int TMEM_COLS_PER_GROUP = 256, A_COL = 96, A_BUF = 80, A_LO = 40;
+  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 128;
+};
+
+struct DivTCMaps { CUtensorMap in, out; };
+
+__global__ void __launch_bounds__(DivTC::THREADS, 1)
+k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg, const float* __restrict__ Dg,
+           long long E) {
+  using L = DivTC;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* sB = smem_raw;
+  unsigned char* groups = smem_raw + L::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(groups + (size_t)L::GROUPS * L::GROUP_BYTES);   // [group][full, mma0, mma1, mma2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * L::GROUPS);
+
+  const int warp = uniform_warp_idx();
+  const int gq = warp >> 2;
+  const int row = threadIdx.x & 127;
+  const bool leader = row == 0;
+
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 4 * L::GROUPS; ++k) mbar_init(&bars[k], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  // operator table [hi | lo]: row n = dof i, k = 40 r + j
+  for (int idx = threadIdx.x; idx < L::N * L::NCHUNK * L::KC; idx += blockDim.x) {
+    const int n = idx / (L::NCHUNK * L::KC), k = idx - n * (L::NCHUNK * L::KC);
+    const int r = k / L::KC, j = k - r * L::KC;
+    const float v = (n < 35 && j < 35) ? Dg[(r * 35 + n) * 35 + j] : 0.f;
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    const int off = (k >> 2) * L::B_LBO + (k & 3) * 4;
+    *reinterpret_cast<uint32_t*>(sB + off + n * 16) = hi;
+    *reinterpret_cast<uint32_t*>(sB + off + (L::N + n) * 16) = lo;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot + (uint32_t)gq * L::TMEM_COLS_PER_GROUP;
+  const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp & 3) * 32u << 16);
+
+  unsigned char* gbase = groups + (size_t)gq * L::GROUP_BYTES;
+  float* slot = reinterpret_cast<float*>(gbase);
+  float* stage = reinterpret_cast<float*>(gbase + L::SLOT_BYTES);
+  uint64_t* full = &bars[4 * gq];
+  uint64_t* mma_done = &bars[4 * gq + 1];                // one per chunk
+  const int bar_id = 1 + gq;
+
+  const long long ntiles = (E + L::TM - 1) / L::TM;
+  const long long tile0 = (long long)blockIdx.x * L::GROUPS + gq, tstride = (long long)gridDim.x * L::GROUPS;
+  constexpr uint32_t idesc_wide = umma_idesc_tf32(L::TM, L::NB), idesc_half = umma_idesc_tf32(L::TM, L::N);
+
+  if (leader && tile0 < ntiles) {
+    mbar_arrive_expect_tx(full, L::SLOT_BYTES);
+    tma_load_3d(slot, &maps.in, 0, (int)(tile0 * (L::TM / 4)), 0, full);
+  }
+  float Jn[9];
+  {
+    const long long e = tile0 * L::TM + row;
+#pragma unroll
+    for (int xr = 0; xr < 9; ++xr) Jn[xr] = (tile0 < ntiles && e < E) ? __ldg(Jg + (long long)xr * E + e) : 0.f;
+  }
+
+  uint32_t it = 0;
+  for (long long tile = tile0; tile < ntiles; tile += tstride, ++it) {
+    float Jr[9];
+#pragma unroll
+    for (int xr = 0; xr < 9; ++xr) Jr[xr] = Jn[xr];
+    {
+      const long long tn = tile + tstride, e = tn * L::TM + row;
+#pragma unroll
+      for (int xr = 0; xr < 9; ++xr) Jn[xr] = (tn < ntiles && e < E) ? __ldg(Jg + (long long)xr * E + e) : 0.f;
+    }
+    mbar_wait(full, it & 1u);
+    const float* su = slot + row * 35;
+#pragma unroll
+    for (int r = 0; r < L::NCHUNK; ++r) {
+      const int buf = r & 1;
+      // chunk r - 2 used the same A buffer: its MMAs must have consumed it
+      if (r == 2) { mbar_wait(&mma_done[0], it & 1u); tc_fence_after(); }
+      const uint32_t a_hi = tmem_lane + L::A_COL + buf * L::A_BUF, a_lo = a_hi + L::A_LO;
+#pragma unroll
+      for (int c = 0; c < L::KC / 8; ++c) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int j = 8 * c + q;
+          float w = 0.f;
+          if (j < 35)
+            w = fmaf(Jr[6 + r], su[2 * L::U_SLAB + j], fmaf(Jr[3 + r], su[L::U_SLAB + j], Jr[r] * su[j]));
+          split_tf32(w, hi[q], lo[q]);
+        }
+        tmem_st8(a_hi + 8 * c, hi);
+        tmem_st8(a_lo + 8 * c, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      group_barrier(bar_id, 128);
+      if (leader) {
+        tc_fence_after();
+        const uint32_t b0 = smem_u32(sB) + r * (L::KC / 4) * L::B_LBO;
+        const uint32_t ta = tmem_base + L::A_COL + buf * L::A_BUF;
+#pragma unroll
+        for (int ks = 0; ks < L::KS_C; ++ks) {
+          const uint64_t db = umma_desc(b0 + ks * 2 * L::B_LBO, L::B_LBO, 128);
+          umma_tf32_ts(tmem_base, ta + 8 * ks, db, idesc_wide, r > 0 || ks > 0);
+          umma_tf32_ts(tmem_base + L::N, ta + L::A_LO + 8 * ks, db, idesc_half, true);
+        }
+        umma_commit(&mma_done[r]);
+        if (r == L::NCHUNK - 1) {
+          // every thread is past its last read of the slot: fetch this group's next tile
+          const long long tl = tile + tstride;
+          if (tl < ntiles) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(full, L::SLOT_BYTES);
+            tma_load_3d(slot, &maps.in, 0, (int)(tl * (L::TM / 4)), 0, full);
+          }
+          tma_store_wait_read();                         // the stage is free again (previous tile's store)
+        }
+      }
+    }
+    mbar_wait(&mma_done[1], it & 1u);
+    mbar_wait(&mma_done[2], it & 1u);
+    tc_fence_after();
+    group_barrier(bar_id, 128);                          // stage free (leader waited above)
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      float m[8], c[8];
+      tmem_ld8(tmem_lane + 8 * q, m);
+      tmem_ld8(tmem_lane + L::N + 8 * q, c);
+      tmem_ld_wait();
+#pragma unroll
+      for (int d = 0; d < 8; ++d)
+        if (8 * q + d < 35) stage[row * 35 + 8 * q + d] = m[d] + c[d];
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    group_barrier(bar_id, 128);
+    if (leader) {
+      tma_store_2d(&maps.out, stage, 0, (int)(tile * (L::TM / 4)));
+      tma_store_commit();
+    }
+  }
+  if (leader) tma_store_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*tmem_slot, 512);
+}
+
+// tensor maps with 128-element boxes (element axis in quads of 140 floats = 560 B rows)
+static bool map32_rows_box(CUtensorMap* tm, const void* base, long long E, int W, int box_quads) {
+  const cuuint64_t dims[2] = {(cuuint64_t)(4 * W), (cuuint64_t)(E / 4)};
+  const cuuint64_t strides[1] = {(cuuint64_t)(16 * W)};
+  const cuuint32_t box[2] = {(cuuint32_t)(4 * W), (cuuint32_t)box_quads};
+  return make_map32(tm, base, 2, dims, strides, box);
+}
+static bool map32_slabs_box(CUtensorMap* tm, const void* base, long long E, int W, int S, int box_quads) {
+  const cuuint64_t dims[3] = {(cuuint64_t)(4 * W), (cuuint64_t)(E / 4), (cuuint64_t)S};
+  const cuuint64_t strides[2] = {(cuuint64_t)(16 * W), (cuuint64_t)E * W * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)(4 * W), (cuuint32_t)box_quads, (cuuint32_t)S};
+  return make_map32(tm, base, 3, dims, strides, box);
+}
+
+// returns FNSM_E_ALIGNMENT when the operands do not qualify (caller falls back to the mma.sync kernel)
+static int launch_grad_tc32(const float* J, const float* D, const float* u, float* out, long long E,
+                            const DevInfo& di, cudaStream_t st) {
+  using L = GradTC;
+  if (E % 4 != 0 || E >= (1LL << 31) - L::TM || !aligned16(u) || !aligned16(out)) return FNSM_E_ALIGNMENT;
+  if (L::SMEM > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
+  GradTCMaps maps;
+  if (!map32_rows_box(&maps.in, u, E, 35, L::TM / 4) || !map32_slabs_box(&maps.out, out, E, 35, 3, L::TM / 4))
+    return FNSM_E_ALIGNMENT;
+  const long long ntiles = (E + L::TM - 1) / L::TM;
+  const long long need = (ntiles + L::GROUPS - 1) / L::GROUPS;
+  const unsigned grid = (unsigned)(di.sms < need ? di.sms : need);
+  if (int rc = set_smem(k_grad_tc32, L::SMEM)) return rc;
+  k_grad_tc32<<<grid, L::THREADS, L::SMEM, st>>>(maps, J, D, E);
+  return post_launch();
+}
+
+static int launch_lift_tc32(int kind, const float* J, const float* O, const OpmatRows& rows, int nrows, long long E,
+                            const DevInfo& di, cudaStream_t st) {
+  using L = LiftTC;
+  const bool fe = kind == FNSM_OP_LIFT_FE;
+  if (E % 4 != 0 || E >= (1LL << 31) - L::TM || (!fe && !aligned16(J))) return FNSM_E_ALIGNMENT;
+  if (L::SMEM > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
+  LiftTCMaps maps;
+  for (int r = 0; r < nrows; ++r) {
+    if (!aligned16(rows.field[r]) || !aligned16(rows.out[r])) return FNSM_E_ALIGNMENT;
+    if (!map32_slabs_box(&maps.in[r], rows.field[r], E, 15, 4, L::TM / 4) ||
+        !map32_rows_box(&maps.out[r], rows.out[r], E, 35, L::TM / 4))
+      return FNSM_E_ALIGNMENT;
+  }
+  const long long ntiles = (E + L::TM - 1) / L::TM;
+  const long long need = (ntiles + L::GROUPS - 1) / L::GROUPS;
+  const unsigned grid = (unsigned)(di.sms < need ? di.sms : need);
+  if (fe) {
+    if (int rc = set_smem(k_lift_tc32<true>, L::SMEM)) return rc;
+    k_lift_tc32<true><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, O, nrows, E);
+  } else {
+    if (int rc = set_smem(k_lift_tc32<false>, L::SMEM)) return rc;
+    k_lift_tc32<false><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, O, nrows, E);
+  }
+  return post_launch();
+}
+
+static int launch_div_tc32(const float* J, const float* D, const float* u, float* out, long long E,
+                           const DevInfo& di, cudaStream_t st) {
+  using L = DivTC;
+  if (E % 4 != 0 || E >= (1LL << 31) - L::TM || !aligned16(u) || !aligned16(out)) return FNSM_E_ALIGNMENT;
+  if (L::SMEM > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
+  DivTCMaps maps;
+  if (!map32_slabs_box(&maps.in, u, E, 35, 3, L::TM / 4) || !map32_rows_box(&maps.out, out, E, 35, L::TM / 4))
+    return FNSM_E_ALIGNMENT;
+  const long long ntiles = (E + L::TM - 1) / L::TM;
+  const long long need = (ntiles + L::GROUPS - 1) / L::GROUPS;
+  const unsigned grid = (unsigned)(di.sms < need ? di.sms : need);
+  if (int rc = set_smem(k_div_tc32, L::SMEM)) return rc;
+  k_div_tc32<<<grid, L::THREADS, L::SMEM, st>>>(maps, J, D, E);
+  return post_launch();
+}
+
+// every row of a batched grad / div is its own launch; lift walks its fields inside one launch
+static int launch_tc32(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows, long long E,
+                       const DevInfo& di, cudaStream_t st) {
+  const float* J = static_cast<const float*>(jac);
+  const float* O = static_cast<const float*>(op);
+  if (kind == FNSM_OP_LIFT_FE || kind == FNSM_OP_LIFT_EF) return launch_lift_tc32(kind, J, O, rows, nrows, E, di, st);
+  for (int r = 0; r < nrows; ++r) {
+    const float* u = static_cast<const float*>(rows.field[r]);
+    float* out = static_cast<float*>(rows.out[r]);
+    const int rc = kind == FNSM_OP_GRAD ? launch_grad_tc32(J, O, u, out, E, di, st) : launch_div_tc32(J, O, u, out, E, di, st);
+    if (rc) return rc;
+  }
+  return FNSM_OK;
+}
+
+}  // namespace fnsm

@@ -67,7 +67,7 @@ enum {
  * Zero in any field = kernel default.
  */
 typedef struct fnsm_cfg {
-  int32_t variant;        /* 0 = auto, 1 = tensor path (DMMA / 3xTF32), 2 = simt      */
+  int32_t variant;        /* 0 = auto, 1 = mma.sync tensor path (DMMA / 3xTF32), 2 = simt, 3 = tcgen05 3xTF32 (fp32) */
   int32_t tile_e;         /* elements per CTA tile                                   */
   int32_t threads;        /* threads per CTA                                         */
   int32_t stages;         /* depth of the global->shared pipeline                    */

@@ -73,13 +73,35 @@ def test_opmat_fp32(cq, n, builder, variant):
     check(builder(dtype="float32"), n, cq, variant=variant)
 
 
-def test_fp32_tensor_path_accuracy_margin(cq):
+@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("n", [4, 128, 132, 1000, 10008, 75776 + 4, 200000])
+@pytest.mark.parametrize("builder", [E.grad, E.div, E.lift_ef, E.lift_fe])
+def test_opmat_fp32_tcgen05(cq, n, builder, variant):
+    # variant 3 = tcgen05 3xTF32 (tiles of 128 elements, two groups per CTA, persistent over 148 SMs:
+    # 75 776 elements = two full rounds of tiles, 200 000 = several tiles per group with a ragged tail);
+    # variant 0 (auto) must pick it for these sizes (n % 4 == 0)
+    check(builder(dtype="float32"), n, cq, variant=variant)
+
+
+@pytest.mark.parametrize("n", [1, 17, 1001])
+@pytest.mark.parametrize("builder", [E.grad, E.div, E.lift_ef, E.lift_fe])
+def test_opmat_fp32_auto_falls_back_when_tma_ineligible(cq, n, builder):
+    # n % 4 != 0: rows are not 16-byte multiples -> auto takes the mma.sync kernel's plain-load path,
+    # an explicit variant 3 reports the alignment error instead of silently running something else
+    e = builder(dtype="float32")
+    check(e, n, cq)
+    with pytest.raises(f.CudaBackendError):
+        check(e, n, cq, variant=3)
+
+
+@pytest.mark.parametrize("variant", [1, 3])
+def test_fp32_tensor_path_accuracy_margin(cq, variant):
     """3xTF32 must sit well inside the fp32 north-star tolerance (1e-5): measure the actual
-    worst relative error of the tensor path against the fp64 oracle on 10 000 elements."""
+    worst relative error of the tensor paths against the fp64 oracle on 10 000 elements."""
     for builder in (E.grad, E.div, E.lift_fe):
         e = builder(dtype="float32")
         ins = np_oracle.generate_input_arrays(e, 10000, 3)
-        got = run(e, ins, cq, variant=1)
+        got = run(e, ins, cq, variant=variant)
         ref = np_oracle.reference_outputs_fp64(e, ins)
         for k in ref:
             rel = np.max(np.abs(got[k].astype(np.float64) - ref[k]) / np.abs(ref[k]))
