@@ -143,6 +143,12 @@ def make_cfg(params: dict[str, Any] | None) -> Any:
         if key == "flags":  # debug bits (bit 0: force the plain-load path of the dmma kernels)
             cfg.reserved[0] = int(val)
             continue
+        if key == "dbgk":  # dmma div: compile-time profiling variants (results invalid)
+            cfg.reserved[2] = int(val)
+            continue
+        if key == "stagger":  # dmma kernels: start-up phase offset (cycles) between warps of one sub-partition
+            cfg.reserved[1] = int(val)
+            continue
         if key not in known:
             raise InvalidParameterError(f"unknown launch parameter '{key}'")
         setattr(cfg, key, int(val))

@@ -125,6 +125,21 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Start-up phase offset.  Warps w, w + 4, w + 8 share a sub-partition and its FP64 pipe; the pipe is
+// arbitrated fairly, so warps that start together stay in lock step (all in their DMMA phase, then
+// all converting / storing with the pipe idle: utilisation N S / (N S + Z) for N warps with S pipe
+// cycles and Z other cycles per item).  Offsetting the first item of the k-th warp of a
+// sub-partition by k * stagger cycles lets one warp's conversion and epilogue run under another's
+// DMMA stream; the offset persists because equal sharing neither grows nor shrinks it.
+__device__ __forceinline__ void stagger_start(int warp, int stagger) {
+  const int rank = warp >> 2;
+  if (stagger > 0 && rank > 0) {
+    const long long t0 = clock64(), dt = (long long)rank * stagger;
+    while (clock64() - t0 < dt) { }
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------ geometry -----
 constexpr int kME = 2;            // element tiles (of 8) per chunk
 constexpr int kCH = 8 * kME;      // elements per chunk / slot
@@ -151,6 +166,7 @@ struct LiftMaps { CUtensorMap jac; CUtensorMap in[8]; CUtensorMap out[8]; };
 constexpr int kFlagTma = 1;        // operands qualify for the TMA path
 constexpr int kFlagNoLoad = 2;     // profiling aid: skip loads  (results invalid)
 constexpr int kFlagNoStore = 4;    // profiling aid: skip stores (results invalid)
+constexpr int kDefaultStagger = 0; // cycles; bits 8.. of `flags` carry the start-up phase offset
 
 // CTA-local dynamic work distribution: CTA b owns the items b, b + G, b + 2G, ...; its warps draw
 // the next k from a shared-memory counter, so a sub-partition hosting fewer warps (NW not a
@@ -210,7 +226,9 @@ __device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps
 // STAGED: results leave through a shared-memory stage + one TMA store (4.4 KB per warp); otherwise
 // straight from the accumulator fragments with 8-byte streaming stores, which frees the shared
 // memory for two more warps (19 KB per warp staged -> 10 warps, 14.6 KB direct -> 12 warps)
-template <int NW, bool STAGED>
+// DBG (profiling aid, results invalid): 1 = no conversion (A fragments = constants), 2 = no left-over
+// DFMAs, 4 = no epilogue
+template <int NW, bool STAGED, int DBG = 0>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, const double* __restrict__ Dg,
            const double* __restrict__ ug, double* __restrict__ outg, long long E, int flags) {
@@ -258,12 +276,18 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
     sL[idx] = (d < kNL && j < 35) ? Dg[(r * 35 + 32 + d) * 35 + j] : 0.0;
   }
   __syncthreads();
+  stagger_start(warp, flags >> 8);
   for (uint32_t n = 0; cur < nchunks; ++n) {
     if (!dbg_noload) mbar_wait(bar, n & 1u);
     // ---- slot -> A fragments (Jacobian folded in) ----
     double a[kME][L::KT];
 #pragma unroll
     for (int m = 0; m < kME; ++m) {
+      if (DBG & 1) {
+#pragma unroll
+        for (int kt = 0; kt < L::KT; ++kt) a[m][kt] = (double)(kt + m) + (double)lane;
+        continue;
+      }
       const int el = chunk_el(g, m);
       double Jr[9];
 #pragma unroll
@@ -288,73 +312,54 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
 
     // ---- DMMA stream ----
     double acc[kME][kNT][2];
-    double accL[1][kME][kNL];      // one chain per value: consecutive links are a whole k-tile (8 DMMAs) apart
 #pragma unroll
-    for (int m = 0; m < kME; ++m) {
+    for (int m = 0; m < kME; ++m)
 #pragma unroll
       for (int nt = 0; nt < kNT; ++nt) { acc[m][nt][0] = 0.0; acc[m][nt][1] = 0.0; }
-#pragma unroll
-      for (int d = 0; d < kNL; ++d) accL[0][m][d] = 0.0;
-    }
     // B fragments are fetched one k-tile ahead of their DMMAs (ptxas otherwise funnels every fragment
     // through one register pair and exposes the LDS latency to each pair of DMMAs)
     const uint32_t bB = smem_u32(sB) + lane * 16, bL = smem_u32(sL) + t * 32;
-    double2 bq[2][2], lq[2][2];
-    bq[0][0] = lds_v2(bB); bq[0][1] = lds_v2(bB + 512);
-    lq[0][0] = lds_v2(bL); lq[0][1] = lds_v2(bL + 16);
+    {
+      double2 bq[2][2];
+      bq[0][0] = lds_v2(bB); bq[0][1] = lds_v2(bB + 512);
 #pragma unroll
-    for (int kt = 0; kt < L::KT; ++kt) {
-      const int c = kt & 1, nx = c ^ 1;
-      if (kt + 1 < L::KT) {
-        bq[nx][0] = lds_v2(bB + (kt + 1) * 1024); bq[nx][1] = lds_v2(bB + (kt + 1) * 1024 + 512);
-        lq[nx][0] = lds_v2(bL + (kt + 1) * 128);  lq[nx][1] = lds_v2(bL + (kt + 1) * 128 + 16);
-      }
+      for (int kt = 0; kt < L::KT; ++kt) {
+        const int c = kt & 1, nx = c ^ 1;
+        if (kt + 1 < L::KT) { bq[nx][0] = lds_v2(bB + (kt + 1) * 1024); bq[nx][1] = lds_v2(bB + (kt + 1) * 1024 + 512); }
 #pragma unroll
-      for (int m = 0; m < kME; ++m) {
-        dmma884(acc[m][0], a[m][kt], bq[c][0].x);
-        dmma884(acc[m][1], a[m][kt], bq[c][0].y);
-        dmma884(acc[m][2], a[m][kt], bq[c][1].x);
-        dmma884(acc[m][3], a[m][kt], bq[c][1].y);
-      }
-#pragma unroll
-      for (int m = 0; m < kME; ++m) {
-        dfma_inplace(accL[0][m][0], a[m][kt], lq[c][0].x);
-        dfma_inplace(accL[0][m][1], a[m][kt], lq[c][0].y);
-        dfma_inplace(accL[0][m][2], a[m][kt], lq[c][1].x);
+        for (int m = 0; m < kME; ++m) {
+          dmma884(acc[m][0], a[m][kt], bq[c][0].x);
+          dmma884(acc[m][1], a[m][kt], bq[c][0].y);
+          dmma884(acc[m][2], a[m][kt], bq[c][1].x);
+          dmma884(acc[m][3], a[m][kt], bq[c][1].y);
+        }
       }
     }
     const long long e0 = cur * kCH;
-    if (STAGED) {
-      // ---- stage the [16][35] block, then one bulk store ----
+    // ---- dofs 0..31 leave the registers first ... ----
+    if (DBG & 4) {
+      double sum = 0.0;
+#pragma unroll
+      for (int m = 0; m < kME; ++m)
+#pragma unroll
+        for (int nt = 0; nt < kNT; ++nt) sum += acc[m][nt][0] + acc[m][nt][1];
+      if (sum == 123.456) outg[0] = sum;
+    } else if (STAGED) {
       if (lane == 0) tma_store_wait_read();          // previous block has left the stage
       __syncwarp();
 #pragma unroll
       for (int m = 0; m < kME; ++m) {
         double* o = stage + chunk_el(g, m) * 35;
-        const double l0 = quad_sum(accL[0][m][0]), l1 = quad_sum(accL[0][m][1]),
-                     l2 = quad_sum(accL[0][m][2]);
 #pragma unroll
-        for (int nt = 0; nt < kNT; ++nt) {
+        for (int nt = 0; nt < kNT; ++nt) {          // rows of 35 doubles: odd elements are only 8-byte aligned
           o[8 * nt + 2 * t] = acc[m][nt][0];
           o[8 * nt + 2 * t + 1] = acc[m][nt][1];
-        }
-        if (t < kNL) o[32 + t] = t == 0 ? l0 : (t == 1 ? l1 : l2);
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (!dbg_nostore) {
-        if (tma) {
-          if (lane == 0) { tma_store_2d(&maps.out, stage, 0, (int)(cur * (kCH / 2))); tma_store_commit(); }
-        } else {
-          flush_plain(outg + e0 * 35, stage, e0, E, lane);
         }
       }
     } else {
 #pragma unroll
       for (int m = 0; m < kME; ++m) {
         const long long e = e0 + chunk_el(g, m);
-        const double l0 = quad_sum(accL[0][m][0]), l1 = quad_sum(accL[0][m][1]),
-                     l2 = quad_sum(accL[0][m][2]);
         if (e < E && !dbg_nostore) {
           double* o = outg + e * 35;
 #pragma unroll
@@ -362,7 +367,65 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
             stg_stream(o + 8 * nt + 2 * t, acc[m][nt][0]);
             stg_stream(o + 8 * nt + 2 * t + 1, acc[m][nt][1]);
           }
-          if (t < kNL) stg_stream(o + 32 + t, t == 0 ? l0 : (t == 1 ? l1 : l2));
+        }
+      }
+    }
+    // ---- ... then dofs 32..34 with DFMA from the same A registers.  A DFMA result is ready after ~30
+    // cycles: with the 32 accumulator registers free again there is room for kLP partial sums per value
+    // (6 kLP independent chains), which makes this tail issue bound (2 cycles per DFMA) instead of
+    // latency bound (ptxas groups the DFMAs behind the DMMAs wherever they are written).
+    constexpr int kLP = 4;
+    double accL[kLP][kME][kNL];
+#pragma unroll
+    for (int p = 0; p < kLP; ++p)
+#pragma unroll
+      for (int m = 0; m < kME; ++m)
+#pragma unroll
+        for (int d = 0; d < kNL; ++d) accL[p][m][d] = 0.0;
+    if (!(DBG & 2)) {
+#pragma unroll
+      for (int kt = 0; kt < L::KT; ++kt) {
+        const double2 l01 = lds_v2(bL + kt * 128), l2x = lds_v2(bL + kt * 128 + 16);
+#pragma unroll
+        for (int m = 0; m < kME; ++m) {
+          accL[kt % kLP][m][0] = fma(a[m][kt], l01.x, accL[kt % kLP][m][0]);
+          accL[kt % kLP][m][1] = fma(a[m][kt], l01.y, accL[kt % kLP][m][1]);
+          accL[kt % kLP][m][2] = fma(a[m][kt], l2x.x, accL[kt % kLP][m][2]);
+        }
+      }
+    }
+    if (DBG & 4) {
+      double sum = 0.0;
+#pragma unroll
+      for (int p = 0; p < kLP; ++p)
+#pragma unroll
+        for (int m = 0; m < kME; ++m)
+#pragma unroll
+          for (int d = 0; d < kNL; ++d) sum += accL[p][m][d];
+      if (sum == 123.456) outg[1] = sum;
+    } else {
+#pragma unroll
+      for (int m = 0; m < kME; ++m) {
+        double l[kNL];
+#pragma unroll
+        for (int d = 0; d < kNL; ++d) l[d] = quad_sum((accL[0][m][d] + accL[1][m][d]) + (accL[2][m][d] + accL[3][m][d]));
+        const double lv = t == 0 ? l[0] : (t == 1 ? l[1] : l[2]);
+        if (STAGED) {
+          if (t < kNL) stage[chunk_el(g, m) * 35 + 32 + t] = lv;
+        } else {
+          const long long e = e0 + chunk_el(g, m);
+          if (e < E && !dbg_nostore && t < kNL) stg_stream(outg + e * 35 + 32 + t, lv);
+        }
+      }
+      if (STAGED) {
+        fence_proxy_async();
+        __syncwarp();
+        if (!dbg_nostore) {
+          if (tma) {
+            if (lane == 0) { tma_store_2d(&maps.out, stage, 0, (int)(cur * (kCH / 2))); tma_store_commit(); }
+          } else {
+            flush_plain(outg + e0 * 35, stage, e0, E, lane);
+          }
         }
       }
     }
@@ -496,6 +559,7 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
     sB[idx] = (v < 27 && i < 35 && j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
   }
   __syncthreads();
+  stagger_start(warp, flags >> 8);
   for (uint32_t n = 0; cur < nchunks; ++n) {
     if (!dbg_noload) mbar_wait(bar, n & 1u);
     double a[kME][L::KT];
@@ -634,6 +698,7 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
     sL[idx] = v;
   }
   __syncthreads();
+  stagger_start(warp, flags >> 8);
   for (uint32_t n = 0; cur < nchunks; ++n) {
     mbar_wait(bar, n & 1u);
     double a[kME][L::KT];
@@ -852,6 +917,10 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
   for (int r = 0; r < nrows; ++r) tma = tma && aligned16(rows.field[r]) && aligned16(rows.out[r]);
   const int dbg = cfg ? cfg->reserved[0] : 0;       // bit 0: force the plain path; bits 1, 2: profiling aids
   if (dbg & 1) tma = false;
+  int stagger = cfg ? cfg->reserved[1] : 0;           // start-up phase offset (cycles); 0 = library default
+  if (stagger == 0) stagger = kDefaultStagger;
+  if (stagger < 0) stagger = 0;                       // negative: off
+  if (stagger > (1 << 20)) stagger = 1 << 20;
   auto grid_for_items = [&](long long nitems) {
     long long grid = di.sms;                          // one persistent CTA per SM
     const long long need = (nitems + NW - 1) / NW;      // no more CTAs than can be kept busy
@@ -878,9 +947,15 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
       bool ok = tma && map_erows(&maps.jac, J, E, 9);
       if (is_div) ok = ok && map_slabs(&maps.in, u, E, 35, 3) && map_rows(&maps.out, out, E, 35);
       else        ok = ok && map_rows(&maps.in, u, E, 35) && map_slabs(&maps.out, out, E, 35, 3);
-      const int flags = (ok ? kFlagTma : 0) | (dbg & (kFlagNoLoad | kFlagNoStore));
+      const int flags = (ok ? kFlagTma : 0) | (dbg & (kFlagNoLoad | kFlagNoStore)) | (stagger << 8);
       if (is_div) {
-        if (staged) {
+        const int dbgk = cfg ? cfg->reserved[2] : 0;
+        if (staged && NW == 10 && dbgk) {
+#define FNSM_DBG_CASE(M) case M: if (int rc = set_smem(k_div_dmma<10, true, M>, smem)) return rc; \
+          k_div_dmma<10, true, M><<<grid_for_items(nchunks), threads, smem, st>>>(maps, J, O, u, out, E, flags); break;
+          switch (dbgk) { FNSM_DBG_CASE(1) FNSM_DBG_CASE(2) FNSM_DBG_CASE(4) FNSM_DBG_CASE(3) FNSM_DBG_CASE(5) FNSM_DBG_CASE(6) FNSM_DBG_CASE(7) default: return FNSM_E_BAD_CONFIG; }
+#undef FNSM_DBG_CASE
+        } else if (staged) {
           if (int rc = set_smem(k_div_dmma<NW, true>, smem)) return rc;
           k_div_dmma<NW, true><<<grid_for_items(nchunks), threads, smem, st>>>(maps, J, O, u, out, E, flags);
         } else {
@@ -902,7 +977,7 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
   bool ok = tma && (kind == FNSM_OP_LIFT_FE ? map_erows(&maps.jac, J, E, 4) : map_rows(&maps.jac, J, E, 4));
   for (int r = 0; r < nrows && ok; ++r)
     ok = map_slabs(&maps.in[r], rows.field[r], E, 15, 4) && map_rows(&maps.out[r], rows.out[r], E, 35);
-  const int flags = ok ? kFlagTma : 0;
+  const int flags = (ok ? kFlagTma : 0) | (stagger << 8);
   if (kind == FNSM_OP_LIFT_FE) {
     if (int rc = set_smem(k_lift_dmma<NW, true>, smem)) return rc;
     k_lift_dmma<NW, true><<<grid, threads, smem, st>>>(maps, J, O, rows, nrows, E, flags);
@@ -919,8 +994,8 @@ static int launch_dmma(int kind, const void* jac, const void* op, const OpmatRow
   (void)n_outer; (void)ni; (void)nj;
   if (cfg && cfg->ctas_per_sm > 1) return FNSM_E_BAD_CONFIG;
   if (cfg && (cfg->stages < 0 || cfg->stages > 1)) return FNSM_E_BAD_CONFIG;
-  // defaults from the round-1 sweep on B200 (profiles/): grad/div 10 warps, lift 12
-  const int dflt = (kind == FNSM_OP_GRAD || kind == FNSM_OP_DIV) ? 320 : 384;
+  // defaults from the round-1 sweeps on B200 (profiles/): grad 10 warps, div 12 (direct stores), lift 12
+  const int dflt = kind == FNSM_OP_GRAD ? 320 : 384;
   const int threads = (cfg && cfg->threads != 0) ? cfg->threads : dflt;
   switch (threads) {
     case 128: return launch_dmma_nw<4>(kind, jac, op, rows, nrows, E, cfg, di, st);
