@@ -38,12 +38,12 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 }
 __device__ __forceinline__ double ldg_stream(const double* p) {
   double v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));   // (L2::evict_first needs a vector type)
   return v;
 }
 __device__ __forceinline__ float ldg_stream(const float* p) {
   float v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void stg_stream(double2* p, double2 v) {

@@ -10,6 +10,7 @@
 #include "opmat_dmma.cuh"
 #include "opmat_tf32.cuh"
 #include "opmat_tc32.cuh"
+#include "opmat_dmma_gen.cuh"
 #include <cstdio>
 #include <cstring>
 
@@ -39,7 +40,12 @@ template <typename T>
 static int launch_simt(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows,
                        int n_outer, int ni, int nj, long long E, const fnsm_cfg* cfg,
                        const DevInfo& di, cudaStream_t st) {
+  // default tile: at least two (element, dof) work items per thread of the 256-thread CTA
   int tile_e = (cfg && cfg->tile_e > 0) ? cfg->tile_e : 16;
+  if (!(cfg && cfg->tile_e > 0)) {
+    const int want = (512 + ni - 1) / ni;
+    tile_e = want <= 16 ? 16 : (want >= 128 ? 128 : (want + 7) / 8 * 8);
+  }
   if (tile_e < 1 || tile_e > 256) return FNSM_E_BAD_CONFIG;
   if (n_outer > 4 && (kind == FNSM_OP_GRAD || kind == FNSM_OP_DIV)) return FNSM_E_UNSUPPORTED;
   size_t smem = 0;
@@ -86,10 +92,12 @@ static int opmat_dispatch(int kind, int dtype, const void* jac, const void* op,
   // both compiled for the p = 4 tet shapes.  auto: fp64 -> 1; fp32 -> 3 when the operands qualify for
   // its TMA tensor maps (E % 4 == 0, 16-byte aligned bases), else 1; other shapes -> 2.
   const bool tensor_ok = dmma_supported(kind, n_outer, ni, nj);
-  if ((variant == 1 || variant == 3) && !tensor_ok) return FNSM_E_UNSUPPORTED;
-  if (variant == 3 && dtype != FNSM_F32) return FNSM_E_UNSUPPORTED;
+  const bool tc_ok = dtype == FNSM_F32 && tc32_supported(kind, n_outer, ni, nj);   // tets p = 1..4
+  const bool gen_ok = dtype == FNSM_F64 && dmma_gen_supported(kind, n_outer, ni, nj);   // fp64 DMMA, tets p = 1..3
+  if (variant == 1 && !tensor_ok && !gen_ok) return FNSM_E_UNSUPPORTED;
+  if (variant == 3 && !tc_ok) return FNSM_E_UNSUPPORTED;
   const bool is_auto = variant == 0;
-  if (is_auto) variant = tensor_ok ? (dtype == FNSM_F32 ? 3 : 1) : 2;
+  if (is_auto) variant = tc_ok ? 3 : ((tensor_ok || gen_ok) ? 1 : 2);
   for (int r0 = 0; r0 < b; r0 += 8) {
     const int nr = (b - r0 < 8) ? (b - r0) : 8;
     OpmatRows rows{};
@@ -100,10 +108,13 @@ static int opmat_dispatch(int kind, int dtype, const void* jac, const void* op,
     }
     int rc;
     if (variant == 1 && dtype == FNSM_F64)
-      rc = launch_dmma(kind, jac, op, rows, nr, n_outer, ni, nj, E, cfg, di, st);
+      rc = tensor_ok ? launch_dmma(kind, jac, op, rows, nr, n_outer, ni, nj, E, cfg, di, st)
+                     : launch_dmma_gen(kind, jac, op, rows, nr, ni, E, cfg, di, st);
     else if (variant == 3) {
-      rc = launch_tc32(kind, jac, op, rows, nr, E, di, st);
-      if (rc == FNSM_E_ALIGNMENT && is_auto) rc = launch_tf32(kind, jac, op, rows, nr, E, cfg, di, st);
+      rc = launch_tc32(kind, jac, op, rows, nr, ni, E, di, st);
+      if (rc == FNSM_E_ALIGNMENT && is_auto)
+        rc = tensor_ok ? launch_tf32(kind, jac, op, rows, nr, E, cfg, di, st)
+                       : launch_simt<float>(kind, jac, op, rows, nr, n_outer, ni, nj, E, cfg, di, st);
     } else if (variant == 1)
       rc = launch_tf32(kind, jac, op, rows, nr, E, cfg, di, st);
     else if (dtype == FNSM_F64)

@@ -95,31 +95,40 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
 }
 
 // ================================================================ GRAD =====
+constexpr int tc_pad(int v, int m) { return (v + m - 1) / m * m; }
+constexpr int tc_max(int a, int b) { return a > b ? a : b; }
+
+// ND = volume dofs per element (p = 1..4 tets: 4, 10, 20, 35); sizes in the comments are for ND = 35
+template <int ND>
 struct GradTC {
   static constexpr int TM = 128;                        // elements per tile
-  static constexpr int K = 40, KS = 5;                  // padded contraction length, k-steps of 8
-  static constexpr int N = 112;                         // columns n = 3 i + r (105 used)
-  static constexpr int NP = 128;                        // column pitch main -> corr (TMEM) = row pitch hi -> lo (table)
+  static constexpr int K = tc_pad(ND, 8), KS = K / 8;   // padded contraction length (40), k-steps of 8
+  static constexpr int N = tc_pad(3 * ND, 16);          // columns n = 3 i + r (112, 105 used)
+  static constexpr int NP = tc_pad(N, 32);              // column pitch main -> corr (TMEM) = row pitch hi -> lo (table)
   static constexpr int NB = NP + N;                     // rows of the operator table: [hi | pad | lo] = 240
   static constexpr int GROUPS = 2, THREADS = GROUPS * 128;
   static constexpr int B_LBO = NB * 16;                 // operator table: addr(n, k) = (k/4) B_LBO + 16 n + 4 (k%4)
   static constexpr int A_LBO = TM * 16;                 // A operand:      addr(e, k) = (k/4) A_LBO + 16 e + 4 (k%4)
   static constexpr int B_BYTES = (K / 4) * B_LBO;       // 35 840
   static constexpr int A_BYTES = (K / 4) * A_LBO;       // 20 480 per half (hi, lo)
-  static constexpr int SLOT_BYTES = TM * 35 * 4;        // 17 920: u rows of one tile
-  static constexpr int STAGE_BYTES = 3 * TM * 35 * 4;   // 53 760: out[x][e][i]; the A operand aliases it
+  static constexpr int SLOT_BYTES = TM * ND * 4;        // 17 920: u rows of one tile
+  static constexpr int OUT_BYTES = 3 * TM * ND * 4;     // 53 760: out[x][e][i]
+  static constexpr int STAGE_BYTES = tc_pad(tc_max(OUT_BYTES, 2 * A_BYTES), 128);   // the A operand aliases the stage
+  static constexpr int NQ = (ND + 7) / 8;               // epilogue passes of 8 dofs (24 columns)
   static constexpr int GROUP_BYTES = 2 * SLOT_BYTES + STAGE_BYTES;
   static constexpr int TMEM_COLS_PER_GROUP = 256;       // 240 used
   static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 128;
-  static_assert(2 * A_BYTES <= STAGE_BYTES, "A operand must fit into the output stage");
+  static_assert(NB <= TMEM_COLS_PER_GROUP && 24 * NQ + NP <= TMEM_COLS_PER_GROUP, "TMEM budget");
+  static_assert(SLOT_BYTES % 128 == 0, "TMA destination alignment");
 };
 
 struct GradTCMaps { CUtensorMap in, out; };
 
-__global__ void __launch_bounds__(GradTC::THREADS, 1)
+template <int ND>
+__global__ void __launch_bounds__(GradTC<ND>::THREADS, 1)
 k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ Jg, const float* __restrict__ Dg,
             long long E) {
-  using L = GradTC;
+  using L = GradTC<ND>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* sB = smem_raw;
   unsigned char* groups = smem_raw + L::B_BYTES;
@@ -141,7 +150,7 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
   for (int idx = threadIdx.x; idx < L::NP * L::K; idx += blockDim.x) {
     const int n = idx / L::K, k = idx - n * L::K;
     const int i = n / 3, r = n - 3 * i;
-    const float v = (n < 105 && k < 35) ? Dg[(r * 35 + i) * 35 + k] : 0.f;
+    const float v = (n < 3 * ND && k < ND) ? Dg[(r * ND + i) * ND + k] : 0.f;
     uint32_t hi, lo;
     split_tf32(v, hi, lo);
     const int off = (k >> 2) * L::B_LBO + (k & 3) * 4;
@@ -202,16 +211,16 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
     group_barrier(bar_id, 128);
     // ---- element row -> A_hi / A_lo (K-major canonical layout: 16-byte k-quads, rows 16 B apart) ----
     {
-      const float* su = slot[s] + row * 35;
+      const float* su = slot[s] + row * ND;
       unsigned char* ahi = stage_b + row * 16;
       unsigned char* alo = ahi + L::A_BYTES;
 #pragma unroll
       for (int kq = 0; kq < L::K / 4; ++kq) {
         uint4 h, l;
-        split_tf32(4 * kq + 0 < 35 ? su[4 * kq + 0] : 0.f, h.x, l.x);
-        split_tf32(4 * kq + 1 < 35 ? su[4 * kq + 1] : 0.f, h.y, l.y);
-        split_tf32(4 * kq + 2 < 35 ? su[4 * kq + 2] : 0.f, h.z, l.z);
-        split_tf32(4 * kq + 3 < 35 ? su[4 * kq + 3] : 0.f, h.w, l.w);
+        split_tf32(4 * kq + 0 < ND ? su[4 * kq + 0] : 0.f, h.x, l.x);
+        split_tf32(4 * kq + 1 < ND ? su[4 * kq + 1] : 0.f, h.y, l.y);
+        split_tf32(4 * kq + 2 < ND ? su[4 * kq + 2] : 0.f, h.z, l.z);
+        split_tf32(4 * kq + 3 < ND ? su[4 * kq + 3] : 0.f, h.w, l.w);
         *reinterpret_cast<uint4*>(ahi + kq * L::A_LBO) = h;
         *reinterpret_cast<uint4*>(alo + kq * L::A_LBO) = l;
       }
@@ -242,7 +251,7 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
     tc_fence_after();
     // ---- TMEM -> registers (8 dofs = 24 columns at a time), J applied, staged as out[x][e][i] ----
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {
+    for (int q = 0; q < L::NQ; ++q) {
       float m[24], c[24];
 #pragma unroll
       for (int p = 0; p < 3; ++p) {
@@ -253,11 +262,11 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
 #pragma unroll
       for (int d = 0; d < 8; ++d) {
         const int i = 8 * q + d;
-        if (i < 35) {
+        if (i < ND) {
           const float T0 = m[3 * d] + c[3 * d], T1 = m[3 * d + 1] + c[3 * d + 1], T2 = m[3 * d + 2] + c[3 * d + 2];
 #pragma unroll
           for (int x = 0; x < 3; ++x)
-            stage[(x * L::TM + row) * 35 + i] = fmaf(Jr[3 * x + 2], T2, fmaf(Jr[3 * x + 1], T1, Jr[3 * x] * T0));
+            stage[(x * L::TM + row) * ND + i] = fmaf(Jr[3 * x + 2], T2, fmaf(Jr[3 * x + 1], T1, Jr[3 * x] * T0));
         }
       }
     }
@@ -281,28 +290,33 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
 // (tcgen05.st) and consumed from there (tcgen05.mma with A in TMEM): no shared-memory round trip.
 // TMEM columns of a group: [0,48) main, [64,112) corr, [128,192) A_hi, [192,256) A_lo.
 // Work item = (tile, field); the face Jacobian of a tile is fetched once for its fields.
+// ND volume dofs, NFD dofs per face (p = 1..4 tets: 4/3, 10/6, 20/10, 35/15), 4 faces
+template <int ND, int NFD>
 struct LiftTC {
   static constexpr int TM = 128;
-  static constexpr int K = 64, KS = 8;
-  static constexpr int N = 48, NP = 64, NB = NP + N;    // operator table rows [hi | pad | lo] = 112
+  static constexpr int K = tc_pad(4 * NFD, 8), KS = K / 8;                      // 64, 8
+  static constexpr int N = tc_pad(ND, 16), NP = tc_pad(N, 32), NB = NP + N;     // 48, 64; table rows [hi | pad | lo] = 112
   static constexpr int GROUPS = 2, THREADS = GROUPS * 128;
   static constexpr int B_LBO = NB * 16;
   static constexpr int B_BYTES = (K / 4) * B_LBO;       // 28 672
-  static constexpr int V_SLAB = TM * 15;                // floats per face
+  static constexpr int V_SLAB = TM * NFD;               // floats per face
   static constexpr int SLOT_BYTES = 4 * V_SLAB * 4;     // 30 720
-  static constexpr int STAGE_BYTES = TM * 35 * 4;       // 17 920
+  static constexpr int STAGE_BYTES = TM * ND * 4;       // 17 920
+  static constexpr int NQ = (ND + 7) / 8;
   static constexpr int GROUP_BYTES = 2 * SLOT_BYTES + STAGE_BYTES;
   static constexpr int TMEM_COLS_PER_GROUP = 256, A_HI_COL = 128, A_LO_COL = 192;
+  static_assert(NB <= A_HI_COL && K <= 64 && K % 8 == 0, "TMEM budget");
+  static_assert(SLOT_BYTES % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA alignment");
   static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 128;
 };
 
 struct LiftTCMaps { CUtensorMap in[8]; CUtensorMap out[8]; };
 
-template <bool FE>
-__global__ void __launch_bounds__(LiftTC::THREADS, 1)
+template <int ND, int NFD, bool FE>
+__global__ void __launch_bounds__(LiftTC<ND, NFD>::THREADS, 1)
 k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ Jg, const float* __restrict__ Og,
             int nrows, long long E) {
-  using L = LiftTC;
+  using L = LiftTC<ND, NFD>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* sB = smem_raw;
   unsigned char* groups = smem_raw + L::B_BYTES;
@@ -323,9 +337,9 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
   // operator table [hi | pad | lo]: row n = dof i, k = 15 f + j
   for (int idx = threadIdx.x; idx < L::NP * L::K; idx += blockDim.x) {
     const int n = idx / L::K, k = idx - n * L::K;
-    const int f = k / 15, j = k - 15 * f;
+    const int f = k / NFD, j = k - NFD * f;
     float v = 0.f;
-    if (n < 35 && k < 60) v = FE ? Og[(n * 4 + f) * 15 + j] : Og[(f * 35 + n) * 15 + j];
+    if (n < ND && k < 4 * NFD) v = FE ? Og[(n * 4 + f) * NFD + j] : Og[(f * ND + n) * NFD + j];
     uint32_t hi, lo;
     split_tf32(v, hi, lo);
     const int off = (k >> 2) * L::B_LBO + (k & 3) * 4;
@@ -393,18 +407,18 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
     mbar_wait(&full[s], (uint32_t)(it >> 1) & 1u);
     // ---- row of the slot -> A_hi / A_lo in TMEM ----
     {
-      const float* sv = slot[s] + row * 15;
+      const float* sv = slot[s] + row * NFD;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {                      // 16 k at a time
-        uint32_t hi[16], lo[16];
+      for (int c = 0; c < L::K / 8; ++c) {               // 8 k at a time
+        uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int k = 16 * c + q, f = k / 15, j = k - 15 * f;
-          const float a = k < 60 ? Jf[f < 4 ? f : 3] * sv[(f < 4 ? f : 3) * L::V_SLAB + j] : 0.f;
+        for (int q = 0; q < 8; ++q) {
+          const int k = 8 * c + q, f = k / NFD, j = k - NFD * f;
+          const float a = k < 4 * NFD ? Jf[f < 4 ? f : 3] * sv[(f < 4 ? f : 3) * L::V_SLAB + j] : 0.f;
           split_tf32(a, hi[q], lo[q]);
         }
-        tmem_st16(tmem_lane + L::A_HI_COL + 16 * c, hi);
-        tmem_st16(tmem_lane + L::A_LO_COL + 16 * c, lo);
+        tmem_st8(tmem_lane + L::A_HI_COL + 8 * c, hi);
+        tmem_st8(tmem_lane + L::A_LO_COL + 8 * c, lo);
       }
       tmem_st_wait();
     }
@@ -427,14 +441,14 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
     tc_fence_after();
     group_barrier(bar_id, 128);                          // ... and every thread knows it
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {
+    for (int q = 0; q < L::NQ; ++q) {
       float m[8], c[8];
       tmem_ld8(tmem_lane + 8 * q, m);
       tmem_ld8(tmem_lane + L::NP + 8 * q, c);
       tmem_ld_wait();
 #pragma unroll
       for (int d = 0; d < 8; ++d)
-        if (8 * q + d < 35) stage[row * 35 + 8 * q + d] = m[d] + c[d];
+        if (8 * q + d < ND) stage[row * ND + 8 * q + d] = m[d] + c[d];
     }
     tc_fence_before();
     fence_proxy_async();
@@ -457,27 +471,32 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
 // writes chunk r into one of two A buffers in TMEM; the elected thread issues that chunk's MMAs while
 // the group folds the next chunk.  TMEM columns of a group: [0,48) main, [48,96) corr,
 // A buffer b: hi [96 + 80 b, +40), lo [136 + 80 b, +40).
+template <int ND>
 struct DivTC {
   static constexpr int TM = 128;
-  static constexpr int KC = 40, KS_C = 5, NCHUNK = 3;   // per chunk: padded length, k-steps
-  static constexpr int N = 48, NB = 2 * N;              // operator table rows [hi | lo] = 96
+  static constexpr int KC = tc_pad(ND, 8), KS_C = KC / 8, NCHUNK = 3;   // per chunk: padded length (40), k-steps
+  static constexpr int N = tc_pad(ND, 16), NB = 2 * N;  // 48; operator table rows [hi | lo] = 96
   static constexpr int GROUPS = 2, THREADS = GROUPS * 128;
   static constexpr int B_LBO = NB * 16;                 // 1536
   static constexpr int B_BYTES = NCHUNK * (KC / 4) * B_LBO;   // 46 080
-  static constexpr int U_SLAB = TM * 35;                // floats per x
+  static constexpr int U_SLAB = TM * ND;                // floats per x
   static constexpr int SLOT_BYTES = 3 * U_SLAB * 4;     // 53 760
-  static constexpr int STAGE_BYTES = TM * 35 * 4;       // 17 920
+  static constexpr int STAGE_BYTES = TM * ND * 4;       // 17 920
+  static constexpr int NQ = (ND + 7) / 8;
   static constexpr int GROUP_BYTES = SLOT_BYTES + STAGE_BYTES;
-  static constexpr int TMEM_COLS_PER_GROUP = 256, A_COL = 96, A_BUF = 80, A_LO = 40;
+  static constexpr int TMEM_COLS_PER_GROUP = 256, A_COL = NB, A_BUF = 2 * KC, A_LO = KC;
+  static_assert(A_COL + 2 * A_BUF <= TMEM_COLS_PER_GROUP, "TMEM budget");
+  static_assert(SLOT_BYTES % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA alignment");
   static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 128;
 };
 
 struct DivTCMaps { CUtensorMap in, out; };
 
-__global__ void __launch_bounds__(DivTC::THREADS, 1)
+template <int ND>
+__global__ void __launch_bounds__(DivTC<ND>::THREADS, 1)
 k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg, const float* __restrict__ Dg,
            long long E) {
-  using L = DivTC;
+  using L = DivTC<ND>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* sB = smem_raw;
   unsigned char* groups = smem_raw + L::B_BYTES;
@@ -499,7 +518,7 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
   for (int idx = threadIdx.x; idx < L::N * L::NCHUNK * L::KC; idx += blockDim.x) {
     const int n = idx / (L::NCHUNK * L::KC), k = idx - n * (L::NCHUNK * L::KC);
     const int r = k / L::KC, j = k - r * L::KC;
-    const float v = (n < 35 && j < 35) ? Dg[(r * 35 + n) * 35 + j] : 0.f;
+    const float v = (n < ND && j < ND) ? Dg[(r * ND + n) * ND + j] : 0.f;
     uint32_t hi, lo;
     split_tf32(v, hi, lo);
     const int off = (k >> 2) * L::B_LBO + (k & 3) * 4;
@@ -546,7 +565,7 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
       for (int xr = 0; xr < 9; ++xr) Jn[xr] = (tn < ntiles && e < E) ? __ldg(Jg + (long long)xr * E + e) : 0.f;
     }
     mbar_wait(full, it & 1u);
-    const float* su = slot + row * 35;
+    const float* su = slot + row * ND;
 #pragma unroll
     for (int r = 0; r < L::NCHUNK; ++r) {
       const int buf = r & 1;
@@ -560,7 +579,7 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
         for (int q = 0; q < 8; ++q) {
           const int j = 8 * c + q;
           float w = 0.f;
-          if (j < 35)
+          if (j < ND)
             w = fmaf(Jr[6 + r], su[2 * L::U_SLAB + j], fmaf(Jr[3 + r], su[L::U_SLAB + j], Jr[r] * su[j]));
           split_tf32(w, hi[q], lo[q]);
         }
@@ -598,14 +617,14 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
     tc_fence_after();
     group_barrier(bar_id, 128);                          // stage free (leader waited above)
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {
+    for (int q = 0; q < L::NQ; ++q) {
       float m[8], c[8];
       tmem_ld8(tmem_lane + 8 * q, m);
       tmem_ld8(tmem_lane + L::N + 8 * q, c);
       tmem_ld_wait();
 #pragma unroll
       for (int d = 0; d < 8; ++d)
-        if (8 * q + d < 35) stage[row * 35 + 8 * q + d] = m[d] + c[d];
+        if (8 * q + d < ND) stage[row * ND + 8 * q + d] = m[d] + c[d];
     }
     tc_fence_before();
     fence_proxy_async();
@@ -635,78 +654,101 @@ static bool map32_slabs_box(CUtensorMap* tm, const void* base, long long E, int 
   return make_map32(tm, base, 3, dims, strides, box);
 }
 
-// returns FNSM_E_ALIGNMENT when the operands do not qualify (caller falls back to the mma.sync kernel)
+// order table of the compiled instantiations: tets p = 1..4
+inline bool tc32_supported(int kind, int n_outer, int ni, int nj) {
+  if (kind == FNSM_OP_GRAD || kind == FNSM_OP_DIV)
+    return n_outer == 3 && ni == nj && (ni == 4 || ni == 10 || ni == 20 || ni == 35);
+  return n_outer == 4 && ((ni == 4 && nj == 3) || (ni == 10 && nj == 6) || (ni == 20 && nj == 10) || (ni == 35 && nj == 15));
+}
+
+// returns FNSM_E_ALIGNMENT when the operands do not qualify (caller falls back to another variant)
+template <int ND>
 static int launch_grad_tc32(const float* J, const float* D, const float* u, float* out, long long E,
                             const DevInfo& di, cudaStream_t st) {
-  using L = GradTC;
+  using L = GradTC<ND>;
   if (E % 4 != 0 || E >= (1LL << 31) - L::TM || !aligned16(u) || !aligned16(out)) return FNSM_E_ALIGNMENT;
   if (L::SMEM > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
   GradTCMaps maps;
-  if (!map32_rows_box(&maps.in, u, E, 35, L::TM / 4) || !map32_slabs_box(&maps.out, out, E, 35, 3, L::TM / 4))
+  if (!map32_rows_box(&maps.in, u, E, ND, L::TM / 4) || !map32_slabs_box(&maps.out, out, E, ND, 3, L::TM / 4))
     return FNSM_E_ALIGNMENT;
   const long long ntiles = (E + L::TM - 1) / L::TM;
   const long long need = (ntiles + L::GROUPS - 1) / L::GROUPS;
   const unsigned grid = (unsigned)(di.sms < need ? di.sms : need);
-  if (int rc = set_smem(k_grad_tc32, L::SMEM)) return rc;
-  k_grad_tc32<<<grid, L::THREADS, L::SMEM, st>>>(maps, J, D, E);
+  if (int rc = set_smem(k_grad_tc32<ND>, L::SMEM)) return rc;
+  k_grad_tc32<ND><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, D, E);
   return post_launch();
 }
 
+template <int ND, int NFD>
 static int launch_lift_tc32(int kind, const float* J, const float* O, const OpmatRows& rows, int nrows, long long E,
                             const DevInfo& di, cudaStream_t st) {
-  using L = LiftTC;
+  using L = LiftTC<ND, NFD>;
   const bool fe = kind == FNSM_OP_LIFT_FE;
   if (E % 4 != 0 || E >= (1LL << 31) - L::TM || (!fe && !aligned16(J))) return FNSM_E_ALIGNMENT;
   if (L::SMEM > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
   LiftTCMaps maps;
   for (int r = 0; r < nrows; ++r) {
     if (!aligned16(rows.field[r]) || !aligned16(rows.out[r])) return FNSM_E_ALIGNMENT;
-    if (!map32_slabs_box(&maps.in[r], rows.field[r], E, 15, 4, L::TM / 4) ||
-        !map32_rows_box(&maps.out[r], rows.out[r], E, 35, L::TM / 4))
+    if (!map32_slabs_box(&maps.in[r], rows.field[r], E, NFD, 4, L::TM / 4) ||
+        !map32_rows_box(&maps.out[r], rows.out[r], E, ND, L::TM / 4))
       return FNSM_E_ALIGNMENT;
   }
   const long long ntiles = (E + L::TM - 1) / L::TM;
   const long long need = (ntiles + L::GROUPS - 1) / L::GROUPS;
   const unsigned grid = (unsigned)(di.sms < need ? di.sms : need);
   if (fe) {
-    if (int rc = set_smem(k_lift_tc32<true>, L::SMEM)) return rc;
-    k_lift_tc32<true><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, O, nrows, E);
+    if (int rc = set_smem(k_lift_tc32<ND, NFD, true>, L::SMEM)) return rc;
+    k_lift_tc32<ND, NFD, true><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, O, nrows, E);
   } else {
-    if (int rc = set_smem(k_lift_tc32<false>, L::SMEM)) return rc;
-    k_lift_tc32<false><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, O, nrows, E);
+    if (int rc = set_smem(k_lift_tc32<ND, NFD, false>, L::SMEM)) return rc;
+    k_lift_tc32<ND, NFD, false><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, O, nrows, E);
   }
   return post_launch();
 }
 
+template <int ND>
 static int launch_div_tc32(const float* J, const float* D, const float* u, float* out, long long E,
                            const DevInfo& di, cudaStream_t st) {
-  using L = DivTC;
+  using L = DivTC<ND>;
   if (E % 4 != 0 || E >= (1LL << 31) - L::TM || !aligned16(u) || !aligned16(out)) return FNSM_E_ALIGNMENT;
   if (L::SMEM > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
   DivTCMaps maps;
-  if (!map32_slabs_box(&maps.in, u, E, 35, 3, L::TM / 4) || !map32_rows_box(&maps.out, out, E, 35, L::TM / 4))
+  if (!map32_slabs_box(&maps.in, u, E, ND, 3, L::TM / 4) || !map32_rows_box(&maps.out, out, E, ND, L::TM / 4))
     return FNSM_E_ALIGNMENT;
   const long long ntiles = (E + L::TM - 1) / L::TM;
   const long long need = (ntiles + L::GROUPS - 1) / L::GROUPS;
   const unsigned grid = (unsigned)(di.sms < need ? di.sms : need);
-  if (int rc = set_smem(k_div_tc32, L::SMEM)) return rc;
-  k_div_tc32<<<grid, L::THREADS, L::SMEM, st>>>(maps, J, D, E);
+  if (int rc = set_smem(k_div_tc32<ND>, L::SMEM)) return rc;
+  k_div_tc32<ND><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, D, E);
   return post_launch();
 }
 
-// every row of a batched grad / div is its own launch; lift walks its fields inside one launch
-static int launch_tc32(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows, long long E,
-                       const DevInfo& di, cudaStream_t st) {
-  const float* J = static_cast<const float*>(jac);
-  const float* O = static_cast<const float*>(op);
-  if (kind == FNSM_OP_LIFT_FE || kind == FNSM_OP_LIFT_EF) return launch_lift_tc32(kind, J, O, rows, nrows, E, di, st);
+template <int ND, int NFD>
+static int launch_tc32_order(int kind, const float* J, const float* O, const OpmatRows& rows, int nrows, long long E,
+                             const DevInfo& di, cudaStream_t st) {
+  if (kind == FNSM_OP_LIFT_FE || kind == FNSM_OP_LIFT_EF) return launch_lift_tc32<ND, NFD>(kind, J, O, rows, nrows, E, di, st);
+  // every row of a batched grad / div is its own launch; lift walks its fields inside one launch
   for (int r = 0; r < nrows; ++r) {
     const float* u = static_cast<const float*>(rows.field[r]);
     float* out = static_cast<float*>(rows.out[r]);
-    const int rc = kind == FNSM_OP_GRAD ? launch_grad_tc32(J, O, u, out, E, di, st) : launch_div_tc32(J, O, u, out, E, di, st);
+    const int rc = kind == FNSM_OP_GRAD ? launch_grad_tc32<ND>(J, O, u, out, E, di, st)
+                                        : launch_div_tc32<ND>(J, O, u, out, E, di, st);
     if (rc) return rc;
   }
   return FNSM_OK;
+}
+
+static int launch_tc32(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows,
+                       int ni, long long E, const DevInfo& di, cudaStream_t st) {
+  const float* J = static_cast<const float*>(jac);
+  const float* O = static_cast<const float*>(op);
+  switch (ni) {
+    case 4: return launch_tc32_order<4, 3>(kind, J, O, rows, nrows, E, di, st);
+    case 10: return launch_tc32_order<10, 6>(kind, J, O, rows, nrows, E, di, st);
+    case 20: return launch_tc32_order<20, 10>(kind, J, O, rows, nrows, E, di, st);
+    case 35: return launch_tc32_order<35, 15>(kind, J, O, rows, nrows, E, di, st);
+    default: return FNSM_E_UNSUPPORTED;
+  }
 }
 
 }  // namespace fnsm

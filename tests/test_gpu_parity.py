@@ -83,6 +83,28 @@ def test_opmat_fp32_tcgen05(cq, n, builder, variant):
     check(builder(dtype="float32"), n, cq, variant=variant)
 
 
+@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("n", [4, 1000, 10008, 200000])
+@pytest.mark.parametrize("order", [(4, 3), (10, 6), (20, 10)])
+def test_opmat_fp32_tcgen05_other_orders(cq, n, order, variant):
+    # tets of order p = 1..3: the tcgen05 kernels are compiled for (volume dofs, face dofs) =
+    # (4, 3), (10, 6), (20, 10), (35, 15)
+    nd, nfd = order
+    check(E.grad(dtype="float32", ndof=nd), n, cq, variant=variant)
+    check(E.div(dtype="float32", ndof=nd), n, cq, variant=variant)
+    check(E.lift_fe(dtype="float32", nvol=nd, nfd=nfd), n, cq, variant=variant)
+    check(E.lift_ef(dtype="float32", nvol=nd, nfd=nfd), n, cq, variant=variant)
+
+
+def test_opmat_fp32_orders_without_tensor_kernel(cq):
+    # no compiled instantiation (2-D triangles, odd sizes): auto takes the simt kernel, variant 3 refuses
+    e = E.grad(dtype="float32", ndim=2, ndof=15)
+    check(e, 1000, cq)
+    with pytest.raises(f.CudaBackendError):
+        check(e, 1000, cq, variant=3)
+    check(E.grad(dtype="float32", ndof=20), 1001, cq)        # n % 4 != 0 and no mma.sync kernel: simt
+
+
 @pytest.mark.parametrize("n", [1, 17, 1001])
 @pytest.mark.parametrize("builder", [E.grad, E.div, E.lift_ef, E.lift_fe])
 def test_opmat_fp32_auto_falls_back_when_tma_ineligible(cq, n, builder):
@@ -118,6 +140,19 @@ def test_grad_batched(cq, n):
 def test_other_orders_take_the_simt_variant(cq, ndof, ndim):
     check(E.grad(ndim=ndim, ndof=ndof), 101, cq)
     check(E.div(ndim=ndim, ndof=ndof), 101, cq)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 1001, 10007, 100000])
+@pytest.mark.parametrize("order", [(4, 3), (10, 6), (20, 10)])
+def test_fp64_dmma_lower_orders(cq, n, order, variant):
+    # tets p = 1..3: variant 1 = the generic fp64 DMMA kernel (opmat_dmma_gen.cuh; plain loads, any n),
+    # variant 2 = simt cross-check, 0 = auto (must take the DMMA kernel and agree)
+    nd, nfd = order
+    check(E.grad(ndof=nd), n, cq, variant=variant)
+    check(E.div(ndof=nd), n, cq, variant=variant)
+    check(E.lift_fe(nvol=nd, nfd=nfd), n, cq, variant=variant)
+    check(E.lift_ef(nvol=nd, nfd=nfd, b=3), n, cq, variant=variant)
 
 
 def test_lift_other_orders(cq):

@@ -24,13 +24,16 @@ IDENTITY = lambda t_unit, insn_match=None, kernel_name=None: t_unit  # noqa: E73
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", type=int, nargs="+", default=[100_000, 4_000_000])
+    ap.add_argument("--orders", action="store_true",
+                    help="tets of order p = 1..3 (4/10/20 volume dofs, 3/6/10 face dofs) instead of the BASELINE shapes")
+    ap.add_argument("--secs", type=float, default=0.5, help="minimum timed seconds per row")
     args = ap.parse_args()
     cq = f.CudaQueue(0)
     fp64 = max(_cabi.measure_peak(0), _cabi.measure_peak(3))
     fp32 = _cabi.measure_peak(1)
     device_info.register_measured_peaks(cq.device.name, float64=fp64, float32=fp32)
     bw = device_info.DEV_TO_PEAK_BW[cq.device.name]
-    measure.N_MIN_SIM_SECS = 0.5
+    measure.N_MIN_SIM_SECS = args.secs
     print(f"# Roofline report, {cq.device.name}: FP64 {fp64:.0f} GFLOP/s, FP32 {fp32:.0f} GFLOP/s (measured in this run), "
           f"HBM {bw:.1f} GB/s (MEASURED_PEAKS.json)\n")
     print("`feinsum_b200.measure.timeit` (validation gate, 5 warm-ups, CUDA events); FLOPs = flop-optimal contraction "
@@ -41,6 +44,13 @@ def main() -> None:
              ("lift ifj,fe,fej->ei b=4", E.lift_fe), ("lift ef,fij,fej->ei b=4", E.lift_ef)]
     rows = []
     for n in args.sizes:
+        if args.orders:
+            for p, nd, nfd in ((1, 4, 3), (2, 10, 6), (3, 20, 10)):
+                for dt in ("float64", "float32"):
+                    rows.append((f"grad p={p}", E.grad(dtype=dt, ndof=nd), dt, n))
+                    rows.append((f"div p={p}", E.div(dtype=dt, ndof=nd), dt, n))
+                    rows.append((f"lift ifj,fe,fej->ei b=4 p={p}", E.lift_fe(dtype=dt, nvol=nd, nfd=nfd), dt, n))
+            continue
         for name, builder in cases:
             for dt in ("float64", "float32"):
                 rows.append((name, builder(dtype=dt), dt, n))
