@@ -95,6 +95,11 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
 }
 
 // ================================================================ GRAD =====
+// A group is WPG (4 or 8) warps: warps w and w + 4 of a group share the TMEM lane quadrant w & 3 (rows
+// 32 (w & 3) .. +31) and split the k-columns of the conversion and the dof columns of the epilogue.
+// (WPG = 8 pays where conversion and epilogue are long -- grad: 94 % vs 90 % -- and costs where the
+// tile already has several barriers -- div: 89 % vs 94 %.)
+
 constexpr int tc_pad(int v, int m) { return (v + m - 1) / m * m; }
 constexpr int tc_max(int a, int b) { return a > b ? a : b; }
 
@@ -106,7 +111,8 @@ struct GradTC {
   static constexpr int N = tc_pad(3 * ND, 16);          // columns n = 3 i + r (112, 105 used)
   static constexpr int NP = tc_pad(N, 32);              // column pitch main -> corr (TMEM) = row pitch hi -> lo (table)
   static constexpr int NB = NP + N;                     // rows of the operator table: [hi | pad | lo] = 240
-  static constexpr int GROUPS = 2, THREADS = GROUPS * 128;
+  static constexpr int WPG = 8, GT = 32 * WPG, NH = WPG / 4;     // warps / threads per group, threads per row
+  static constexpr int GROUPS = 2, THREADS = GROUPS * GT;
   static constexpr int B_LBO = NB * 16;                 // operator table: addr(n, k) = (k/4) B_LBO + 16 n + 4 (k%4)
   static constexpr int A_LBO = TM * 16;                 // A operand:      addr(e, k) = (k/4) A_LBO + 16 e + 4 (k%4)
   static constexpr int B_BYTES = (K / 4) * B_LBO;       // 35 840
@@ -136,9 +142,10 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * L::GROUPS);
 
   const int warp = uniform_warp_idx();
-  const int gq = warp >> 2;                              // group
-  const int row = threadIdx.x & 127;                     // element row of the tile = TMEM lane
-  const bool leader = row == 0;
+  const int gq = warp / L::WPG, wq = warp - gq * L::WPG; // group, warp in group
+  const int row = (wq & 3) * 32 + (threadIdx.x & 31);    // element row of the tile = TMEM lane
+  const int half = L::NH == 1 ? 0 : wq >> 2;             // which share of the row's columns (constant 0 for WPG = 4)
+  const bool leader = wq == 0 && (threadIdx.x & 31) == 0;
 
   if (threadIdx.x == 0) {
     for (int k = 0; k < 3 * L::GROUPS; ++k) mbar_init(&bars[k], 1);
@@ -208,14 +215,16 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
     mbar_wait(&full[s], (it >> 1) & 1u);
     // the A operand aliases the output stage: the previous tile's bulk store must have read it out
     if (leader) tma_store_wait_read();
-    group_barrier(bar_id, 128);
+    group_barrier(bar_id, L::GT);
     // ---- element row -> A_hi / A_lo (K-major canonical layout: 16-byte k-quads, rows 16 B apart) ----
     {
       const float* su = slot[s] + row * ND;
       unsigned char* ahi = stage_b + row * 16;
       unsigned char* alo = ahi + L::A_BYTES;
 #pragma unroll
-      for (int kq = 0; kq < L::K / 4; ++kq) {
+      for (int kq0 = 0; kq0 < L::K / 4; kq0 += L::NH) {
+        const int kq = kq0 + half;
+        if (kq >= L::K / 4) break;
         uint4 h, l;
         split_tf32(4 * kq + 0 < ND ? su[4 * kq + 0] : 0.f, h.x, l.x);
         split_tf32(4 * kq + 1 < ND ? su[4 * kq + 1] : 0.f, h.y, l.y);
@@ -227,7 +236,7 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
     }
     fence_proxy_async();                                 // generic-proxy writes -> tensor core / TMA reads
     tc_fence_before();
-    group_barrier(bar_id, 128);
+    group_barrier(bar_id, L::GT);
     if (leader) {
       tc_fence_after();
       const uint32_t a_hi = smem_u32(stage_b), a_lo = a_hi + L::A_BYTES, b0 = smem_u32(sB);
@@ -251,7 +260,9 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
     tc_fence_after();
     // ---- TMEM -> registers (8 dofs = 24 columns at a time), J applied, staged as out[x][e][i] ----
 #pragma unroll
-    for (int q = 0; q < L::NQ; ++q) {
+    for (int q0 = 0; q0 < L::NQ; q0 += L::NH) {
+      const int q = q0 + half;
+      if (q >= L::NQ) break;
       float m[24], c[24];
 #pragma unroll
       for (int p = 0; p < 3; ++p) {
@@ -272,7 +283,7 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
     }
     tc_fence_before();                                   // TMEM reads done before the next tile's MMAs
     fence_proxy_async();
-    group_barrier(bar_id, 128);
+    group_barrier(bar_id, L::GT);
     if (leader) {
       tma_store_3d(&maps.out, stage, 0, (int)(tile * (L::TM / 4)), 0);
       tma_store_commit();
@@ -296,7 +307,8 @@ struct LiftTC {
   static constexpr int TM = 128;
   static constexpr int K = tc_pad(4 * NFD, 8), KS = K / 8;                      // 64, 8
   static constexpr int N = tc_pad(ND, 16), NP = tc_pad(N, 32), NB = NP + N;     // 48, 64; table rows [hi | pad | lo] = 112
-  static constexpr int GROUPS = 2, THREADS = GROUPS * 128;
+  static constexpr int WPG = 4, GT = 32 * WPG, NH = WPG / 4;
+  static constexpr int GROUPS = 2, THREADS = GROUPS * GT;
   static constexpr int B_LBO = NB * 16;
   static constexpr int B_BYTES = (K / 4) * B_LBO;       // 28 672
   static constexpr int V_SLAB = TM * NFD;               // floats per face
@@ -324,9 +336,10 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * L::GROUPS);
 
   const int warp = uniform_warp_idx();
-  const int gq = warp >> 2;
-  const int row = threadIdx.x & 127;
-  const bool leader = row == 0;
+  const int gq = warp / L::WPG, wq = warp - gq * L::WPG;
+  const int row = (wq & 3) * 32 + (threadIdx.x & 31);
+  const int half = L::NH == 1 ? 0 : wq >> 2;
+  const bool leader = wq == 0 && (threadIdx.x & 31) == 0;
 
   if (threadIdx.x == 0) {
     for (int k = 0; k < 3 * L::GROUPS; ++k) mbar_init(&bars[k], 1);
@@ -409,7 +422,9 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
     {
       const float* sv = slot[s] + row * NFD;
 #pragma unroll
-      for (int c = 0; c < L::K / 8; ++c) {               // 8 k at a time
+      for (int c0 = 0; c0 < L::K / 8; c0 += L::NH) {     // 8 k at a time
+        const int c = c0 + half;
+        if (c >= L::K / 8) break;
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -423,7 +438,7 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
       tmem_st_wait();
     }
     tc_fence_before();
-    group_barrier(bar_id, 128);
+    group_barrier(bar_id, L::GT);
     if (leader) {
       tc_fence_after();
       const uint32_t b0 = smem_u32(sB);
@@ -439,9 +454,11 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
     }
     mbar_wait(mma_done, (uint32_t)it & 1u);
     tc_fence_after();
-    group_barrier(bar_id, 128);                          // ... and every thread knows it
+    group_barrier(bar_id, L::GT);                          // ... and every thread knows it
 #pragma unroll
-    for (int q = 0; q < L::NQ; ++q) {
+    for (int q0 = 0; q0 < L::NQ; q0 += L::NH) {
+      const int q = q0 + half;
+      if (q >= L::NQ) break;
       float m[8], c[8];
       tmem_ld8(tmem_lane + 8 * q, m);
       tmem_ld8(tmem_lane + L::NP + 8 * q, c);
@@ -452,7 +469,7 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
     }
     tc_fence_before();
     fence_proxy_async();
-    group_barrier(bar_id, 128);
+    group_barrier(bar_id, L::GT);
     if (leader) {
       tma_store_2d(&maps.out[fld], stage, 0, (int)(tile * (L::TM / 4)));
       tma_store_commit();
@@ -476,7 +493,8 @@ struct DivTC {
   static constexpr int TM = 128;
   static constexpr int KC = tc_pad(ND, 8), KS_C = KC / 8, NCHUNK = 3;   // per chunk: padded length (40), k-steps
   static constexpr int N = tc_pad(ND, 16), NB = 2 * N;  // 48; operator table rows [hi | lo] = 96
-  static constexpr int GROUPS = 2, THREADS = GROUPS * 128;
+  static constexpr int WPG = 4, GT = 32 * WPG, NH = WPG / 4;
+  static constexpr int GROUPS = 2, THREADS = GROUPS * GT;
   static constexpr int B_LBO = NB * 16;                 // 1536
   static constexpr int B_BYTES = NCHUNK * (KC / 4) * B_LBO;   // 46 080
   static constexpr int U_SLAB = TM * ND;                // floats per x
@@ -504,9 +522,10 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * L::GROUPS);
 
   const int warp = uniform_warp_idx();
-  const int gq = warp >> 2;
-  const int row = threadIdx.x & 127;
-  const bool leader = row == 0;
+  const int gq = warp / L::WPG, wq = warp - gq * L::WPG;
+  const int row = (wq & 3) * 32 + (threadIdx.x & 31);
+  const int half = L::NH == 1 ? 0 : wq >> 2;
+  const bool leader = wq == 0 && (threadIdx.x & 31) == 0;
 
   if (threadIdx.x == 0) {
     for (int k = 0; k < 4 * L::GROUPS; ++k) mbar_init(&bars[k], 1);
@@ -573,7 +592,9 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
       if (r == 2) { mbar_wait(&mma_done[0], it & 1u); tc_fence_after(); }
       const uint32_t a_hi = tmem_lane + L::A_COL + buf * L::A_BUF, a_lo = a_hi + L::A_LO;
 #pragma unroll
-      for (int c = 0; c < L::KC / 8; ++c) {
+      for (int c0 = 0; c0 < L::KC / 8; c0 += L::NH) {
+        const int c = c0 + half;
+        if (c >= L::KC / 8) break;
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -588,7 +609,7 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
       }
       tmem_st_wait();
       tc_fence_before();
-      group_barrier(bar_id, 128);
+      group_barrier(bar_id, L::GT);
       if (leader) {
         tc_fence_after();
         const uint32_t b0 = smem_u32(sB) + r * (L::KC / 4) * L::B_LBO;
@@ -615,9 +636,11 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
     mbar_wait(&mma_done[1], it & 1u);
     mbar_wait(&mma_done[2], it & 1u);
     tc_fence_after();
-    group_barrier(bar_id, 128);                          // stage free (leader waited above)
+    group_barrier(bar_id, L::GT);                          // stage free (leader waited above)
 #pragma unroll
-    for (int q = 0; q < L::NQ; ++q) {
+    for (int q0 = 0; q0 < L::NQ; q0 += L::NH) {
+      const int q = q0 + half;
+      if (q >= L::NQ) break;
       float m[8], c[8];
       tmem_ld8(tmem_lane + 8 * q, m);
       tmem_ld8(tmem_lane + L::N + 8 * q, c);
@@ -628,7 +651,7 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
     }
     tc_fence_before();
     fence_proxy_async();
-    group_barrier(bar_id, 128);
+    group_barrier(bar_id, L::GT);
     if (leader) {
       tma_store_2d(&maps.out, stage, 0, (int)(tile * (L::TM / 4)));
       tma_store_commit();
