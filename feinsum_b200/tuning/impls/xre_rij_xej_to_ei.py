@@ -6,7 +6,9 @@ n_e_per_wg / nwork_items_per_e / i_tiles / j_tiles were for its generated code):
 * ``warps``   -- warps of the persistent CTA (one CTA per SM); every warp owns a shared-memory
   slot + output stage, so the legal maximum is set by the 227 KB of an SM
   (``FNSM_E_BAD_CONFIG`` -> InvalidParameterError above it);
-* ``variant`` -- 1 = tensor path (fp64 DMMA / fp32 3xTF32, p = 4 shapes), 2 = simt fallback.
+* ``variant`` -- 1 = mma.sync tensor path (fp64 DMMA / fp32 3xTF32), 2 = simt fallback, 3 = tcgen05 3xTF32 with
+  TMEM accumulators (fp32 only; no further tunables: ``warps`` is ignored).  fp64 einsums tune over variant 1,
+  fp32 einsums over 1..3.
 """
 
 from typing import Any
@@ -14,11 +16,18 @@ from typing import Any
 from feinsum_b200.codegen.cuda import CudaProgram
 from feinsum_b200.tuning import IntParameter, transform_param
 
+def _variant_space(ensm: Any) -> IntParameter:
+    import numpy as np
+
+    fp32 = all(np.dtype(dt) == np.float32 for dt in ensm.arg_to_dtype.values())
+    return IntParameter(1, 3) if fp32 else IntParameter(1, 1)
+
+
 KERNEL_ID = "div"
 
 
 @transform_param("warps", lambda ensm: IntParameter(8, 16))
-@transform_param("variant", lambda ensm: IntParameter(1, 1))
+@transform_param("variant", _variant_space)
 def transform(program: CudaProgram, warps: int, variant: int = 1, insn_match: Any | None = None,
               kernel_name: str | None = None) -> CudaProgram:
     if program.kernel_id != KERNEL_ID:
