@@ -73,39 +73,64 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
 
   const long long nchunks = (E + kCH - 1) / kCH;
   const long long wstride = (long long)gridDim.x * L::NW;
-  for (long long chunk = (long long)blockIdx.x * L::NW + warp; chunk < nchunks; chunk += wstride) {
+  const long long chunk0 = (long long)blockIdx.x * L::NW + warp;
+  const long long my_chunks = chunk0 < nchunks ? (nchunks - chunk0 + wstride - 1) / wstride : 0;
+  const long long nitems = my_chunks * nrows;             // item = (chunk, row of the batched einsum)
+
+  // Software pipeline: the element data (and, for the first row of a chunk, the Jacobian entries) of
+  // item n + 1 are fetched into registers with coalesced loads while item n is being computed.
+  constexpr int NIN = L::IN_DOUBLES / 32, NJR = (L::J_DOUBLES + 31) / 32;
+  static_assert(L::IN_DOUBLES % 32 == 0, "slot size must be a multiple of the warp size");
+  double rin[NIN], rj[NJR];
+  auto fetch = [&](long long item) {
+    const long long chunk = chunk0 + (item / nrows) * wstride;
+    const int row = (int)(item % nrows);
     const long long e0 = chunk * kCH;
     const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-    // ---- Jacobian entries of the chunk: sJ[xr][el] ----
-    if (L::LIFT && !FE) {
-      for (int k = lane; k < 4 * kCH; k += 32) {         // J(E, 4): contiguous, transposed on the way in
-        const int el = k >> 2, f = k & 3;
-        sJ[f * kCH + el] = el < ne ? ldg_stream(Jg + e0 * 4 + k) : 0.0;
-      }
-    } else {
-      constexpr int NJ = L::LIFT ? 4 : 9;
-      for (int k = lane; k < NJ * kCH; k += 32) {
-        const int xr = k / kCH, el = k - xr * kCH;
-        sJ[k] = el < ne ? ldg_stream(Jg + (long long)xr * E + e0 + el) : 0.0;
+    const double* __restrict__ in = static_cast<const double*>(rows.field[row]);
+    constexpr int W = L::GRAD || L::DIV ? ND : NFD;        // row length of one slab
+#pragma unroll
+    for (int q = 0; q < NIN; ++q) {
+      const int k = lane + 32 * q, slab = k / (kCH * W), kk = k - slab * (kCH * W);
+      rin[q] = kk < ne * W ? ldg_stream(in + ((long long)slab * E + e0) * W + kk) : 0.0;
+    }
+    if (row == 0) {
+#pragma unroll
+      for (int q = 0; q < NJR; ++q) {
+        const int k = lane + 32 * q;
+        double v = 0.0;
+        if (L::LIFT && !FE) {
+          if (k < L::J_DOUBLES && (k >> 2) < ne) v = ldg_stream(Jg + e0 * 4 + k);       // J(E, 4): contiguous
+        } else {
+          const int xr = k / kCH, el = k - xr * kCH;
+          if (k < L::J_DOUBLES && el < ne) v = ldg_stream(Jg + (long long)xr * E + e0 + el);
+        }
+        rj[q] = v;
       }
     }
-    for (int row = 0; row < nrows; ++row) {
-      const double* __restrict__ in = static_cast<const double*>(rows.field[row]);
-      double* __restrict__ out = static_cast<double*>(rows.out[row]);
-      // ---- element data: coalesced, zero filled past E ----
-      if (L::GRAD) {
-        for (int k = lane; k < kCH * ND; k += 32) s[k] = k < ne * ND ? ldg_stream(in + e0 * ND + k) : 0.0;
-      } else if (L::DIV) {
+  };
+  if (nitems > 0) fetch(0);
+  for (long long item = 0; item < nitems; ++item) {
+    const long long chunk = chunk0 + (item / nrows) * wstride;
+    const int row = (int)(item % nrows);
+    const long long e0 = chunk * kCH;
+    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+    double* __restrict__ out = static_cast<double*>(rows.out[row]);
+    {
+      // ---- registers -> slot (the previous item's stores have been issued; its slot reads are done) ----
 #pragma unroll
-        for (int x = 0; x < 3; ++x)
-          for (int k = lane; k < kCH * ND; k += 32)
-            s[x * kCH * ND + k] = k < ne * ND ? ldg_stream(in + ((long long)x * E + e0) * ND + k) : 0.0;
-      } else {
+      for (int q = 0; q < NIN; ++q) s[lane + 32 * q] = rin[q];
+      if (row == 0) {
 #pragma unroll
-        for (int f = 0; f < 4; ++f)
-          for (int k = lane; k < kCH * NFD; k += 32)
-            s[f * kCH * NFD + k] = k < ne * NFD ? ldg_stream(in + ((long long)f * E + e0) * NFD + k) : 0.0;
+        for (int q = 0; q < NJR; ++q) {
+          const int k = lane + 32 * q;
+          if (k < L::J_DOUBLES) {
+            if (L::LIFT && !FE) sJ[(k & 3) * kCH + (k >> 2)] = rj[q];                    // transposed to [f][el]
+            else sJ[k] = rj[q];
+          }
+        }
       }
+      if (item + 1 < nitems) fetch(item + 1);
       __syncwarp();
       // ---- A fragments: lane (g, t) holds rows el = g + 8 m, k = (kt, t) ----
       double a[kME][L::KT];
@@ -182,7 +207,7 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
           stg_stream(out + e0 * ND + idx, stage[el * L::PITCH + i]);
         }
       }
-      __syncwarp();                                       // slot and stage are rewritten by the next row / chunk
+      __syncwarp();                                       // slot and stage are rewritten by the next item
     }
   }
 }
