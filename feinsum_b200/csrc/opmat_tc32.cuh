@@ -222,9 +222,8 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
       unsigned char* ahi = stage_b + row * 16;
       unsigned char* alo = ahi + L::A_BYTES;
 #pragma unroll
-      for (int kq0 = 0; kq0 < L::K / 4; kq0 += L::NH) {
-        const int kq = kq0 + half;
-        if (kq >= L::K / 4) break;
+      for (int kq = 0; kq < L::K / 4; ++kq) {
+        if (L::NH > 1 && (kq % L::NH) != half) continue;   // warp-uniform; kq stays a compile-time constant
         uint4 h, l;
         split_tf32(4 * kq + 0 < ND ? su[4 * kq + 0] : 0.f, h.x, l.x);
         split_tf32(4 * kq + 1 < ND ? su[4 * kq + 1] : 0.f, h.y, l.y);
@@ -260,9 +259,8 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
     tc_fence_after();
     // ---- TMEM -> registers (8 dofs = 24 columns at a time), J applied, staged as out[x][e][i] ----
 #pragma unroll
-    for (int q0 = 0; q0 < L::NQ; q0 += L::NH) {
-      const int q = q0 + half;
-      if (q >= L::NQ) break;
+    for (int q = 0; q < L::NQ; ++q) {
+      if (L::NH > 1 && (q % L::NH) != half) continue;   // warp-uniform; q stays a compile-time constant
       float m[24], c[24];
 #pragma unroll
       for (int p = 0; p < 3; ++p) {
@@ -422,9 +420,8 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
     {
       const float* sv = slot[s] + row * NFD;
 #pragma unroll
-      for (int c0 = 0; c0 < L::K / 8; c0 += L::NH) {     // 8 k at a time
-        const int c = c0 + half;
-        if (c >= L::K / 8) break;
+      for (int c = 0; c < L::K / 8; ++c) {     // 8 k at a time
+        if (L::NH > 1 && (c % L::NH) != half) continue;   // warp-uniform; c stays a compile-time constant
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -456,9 +453,8 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
     tc_fence_after();
     group_barrier(bar_id, L::GT);                          // ... and every thread knows it
 #pragma unroll
-    for (int q0 = 0; q0 < L::NQ; q0 += L::NH) {
-      const int q = q0 + half;
-      if (q >= L::NQ) break;
+    for (int q = 0; q < L::NQ; ++q) {
+      if (L::NH > 1 && (q % L::NH) != half) continue;   // warp-uniform; q stays a compile-time constant
       float m[8], c[8];
       tmem_ld8(tmem_lane + 8 * q, m);
       tmem_ld8(tmem_lane + L::NP + 8 * q, c);
@@ -592,9 +588,8 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
       if (r == 2) { mbar_wait(&mma_done[0], it & 1u); tc_fence_after(); }
       const uint32_t a_hi = tmem_lane + L::A_COL + buf * L::A_BUF, a_lo = a_hi + L::A_LO;
 #pragma unroll
-      for (int c0 = 0; c0 < L::KC / 8; c0 += L::NH) {
-        const int c = c0 + half;
-        if (c >= L::KC / 8) break;
+      for (int c = 0; c < L::KC / 8; ++c) {
+        if (L::NH > 1 && (c % L::NH) != half) continue;   // warp-uniform; c stays a compile-time constant
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -638,9 +633,8 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
     tc_fence_after();
     group_barrier(bar_id, L::GT);                          // stage free (leader waited above)
 #pragma unroll
-    for (int q0 = 0; q0 < L::NQ; q0 += L::NH) {
-      const int q = q0 + half;
-      if (q >= L::NQ) break;
+    for (int q = 0; q < L::NQ; ++q) {
+      if (L::NH > 1 && (q % L::NH) != half) continue;   // warp-uniform; q stays a compile-time constant
       float m[8], c[8];
       tmem_ld8(tmem_lane + 8 * q, m);
       tmem_ld8(tmem_lane + L::N + 8 * q, c);
