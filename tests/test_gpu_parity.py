@@ -96,13 +96,29 @@ def test_opmat_fp32_tcgen05_other_orders(cq, n, order, variant):
     check(E.lift_ef(dtype="float32", nvol=nd, nfd=nfd), n, cq, variant=variant)
 
 
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 1001, 10007, 100000])
+@pytest.mark.parametrize("order", [(4, 3), (10, 6), (20, 10)])
+def test_fp32_generic_tensor_kernel_lower_orders(cq, n, order):
+    # variant 1 at p = 1..3 = the generic 3xTF32 mma.sync kernel (opmat_tf32_gen.cuh; plain loads, any n);
+    # it is also what auto falls back to when n % 4 != 0 rules the tcgen05 kernels out
+    nd, nfd = order
+    for e in (E.grad(dtype="float32", ndof=nd), E.div(dtype="float32", ndof=nd),
+              E.lift_fe(dtype="float32", nvol=nd, nfd=nfd), E.lift_ef(dtype="float32", nvol=nd, nfd=nfd, b=3)):
+        check(e, n, cq, variant=1)
+    ins = np_oracle.generate_input_arrays(E.div(dtype="float32", ndof=nd), 4000, 5)
+    got = run(E.div(dtype="float32", ndof=nd), ins, cq, variant=1)
+    ref = np_oracle.reference_outputs_fp64(E.div(dtype="float32", ndof=nd), ins)
+    for k in ref:
+        assert np.max(np.abs(got[k].astype(np.float64) - ref[k]) / np.abs(ref[k])) < 3e-6
+
+
 def test_opmat_fp32_orders_without_tensor_kernel(cq):
     # no compiled instantiation (2-D triangles, odd sizes): auto takes the simt kernel, variant 3 refuses
     e = E.grad(dtype="float32", ndim=2, ndof=15)
     check(e, 1000, cq)
     with pytest.raises(f.CudaBackendError):
         check(e, 1000, cq, variant=3)
-    check(E.grad(dtype="float32", ndof=20), 1001, cq)        # n % 4 != 0 and no mma.sync kernel: simt
+    check(E.grad(dtype="float32", ndof=20), 1001, cq)        # n % 4 != 0: the generic kernel takes any n
 
 
 @pytest.mark.parametrize("n", [1, 17, 1001])
