@@ -13,7 +13,9 @@ parameters, ``transform_id`` names a launch-configuration module under
 variant choices; the new columns keep what the B200 report needs (elements
 timed, GFLOP/s, GB/s, fraction of the roofline).  Table
 ``FEINSUM_CUDA_FACTS``; the reference's ``FEINSUM_TIMING_FACTS`` rows (Titan V,
-loopy) are not comparable and are not imported.
+loopy) are not comparable and are not imported.  The shipped default database
+(``data/cuda_facts_v1.sqlite``) holds the autotuner's B200 facts for the BASELINE
+einsums (``tools/populate_db.py``).
 """
 
 from __future__ import annotations

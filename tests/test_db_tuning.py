@@ -157,3 +157,26 @@ def test_autotune_tuple_parameter_module(tmp_path, monkeypatch):
     facts = f.query(expr, FakeCLDevice("NVIDIA B200"), database=db)
     assert {q.transform_params["wg_size"] for q in facts} == {(a, b) for a in (8, 9) for b in (8, 9, 10)}
     assert all(os.path.isabs(q.transform_id) for q in facts)      # module outside tuning/impls -> absolute path
+
+
+def test_shipped_database_has_b200_facts():
+    """The package ships ``feinsum_b200/data/cuda_facts_v1.sqlite`` (filled by ``tools/populate_db.py`` on a
+    B200: autotuner over the BASELINE einsums at E = 4 000 000 and 100 000) -- the counterpart of the
+    reference's ``data/transform_archive_v5.sqlite``; ``retrieve`` with the default database must hand back
+    a launch configuration for every BASELINE einsum, found under any renaming of it."""
+    from feinsum_b200.codegen.cuda import generate_cuda
+
+    dev = FakeCLDevice("NVIDIA B200")
+    assert os.path.exists(f.DEFAULT_DB)
+    for dt in ("float64", "float32"):
+        for e in (E.grad(dtype=dt), E.div(dtype=dt), E.lift_fe(dtype=dt), E.lift_ef(dtype=dt), E.tensor_product(0, 8, dt)):
+            facts = f.query(e, dev)
+            assert facts and {q.n_elements for q in facts} == {100_000, 4_000_000}
+            best = f.retrieve(e, dev)
+            assert best(generate_cuda(e)).kernel_id == generate_cuda(e).kernel_id
+    fp32_best = min((q for q in f.query(E.div(dtype="float32"), dev) if q.n_elements == 4_000_000),
+                    key=lambda q: q.runtime_in_sec)
+    assert fp32_best.transform_params["variant"] == 3          # tcgen05 wins the fp32 search
+    renamed = f.einsum("abn,nq,bpq->anp", f.array("Jac", (3, 3, "N")), f.array("v", ("N", 35)), f.array("Dmat", (3, 35, 35)))
+    assert len(f.query(renamed, dev)) == len(f.query(E.grad(), dev))
+    assert len(f.get_timed_einsums_in_db(dev)) == 10

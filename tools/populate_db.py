@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Populate the facts database shipped with the package (``feinsum_b200/data/cuda_facts_v1.sqlite``) by
+running the autotuner over the BASELINE einsums on the current GPU -- the CUDA counterpart of the
+reference's ``data/transform_archive_v5.sqlite`` (reference ``tuning/__init__.py:485-633`` fills that one).
+
+    python tools/populate_db.py [--db PATH] [--elements 4000000] [--secs 0.15]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import feinsum_b200 as f  # noqa: E402
+from feinsum_b200 import measure, sql_utils, tuning  # noqa: E402
+from tests import einsums as E  # noqa: E402
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--db", default=sql_utils.DEFAULT_DB)
+    ap.add_argument("--elements", type=int, nargs="+", default=[4_000_000, 100_000])
+    ap.add_argument("--secs", type=float, default=0.15)
+    args = ap.parse_args()
+    measure.N_MIN_SIM_SECS = args.secs
+    cq = f.CudaQueue(0)
+    impls = os.path.join(os.path.dirname(os.path.abspath(tuning.__file__)), "impls")
+    cases = []
+    for dt in ("float64", "float32"):
+        cases += [(E.grad(dtype=dt), "xre_rij_ej_to_xei.py"), (E.div(dtype=dt), "xre_rij_xej_to_ei.py"),
+                  (E.lift_fe(dtype=dt), "ifj_fe_fej_to_ei.py"), (E.lift_ef(dtype=dt), "ef_fij_fej_to_ei.py"),
+                  (E.tensor_product(0, 8, dt), "eabc_ia_to_eibc.py")]
+    for n in args.elements:
+        for e, mod in cases:
+            best = tuning.autotune(e, os.path.join(impls, mod), cq, db_path=args.db, long_dim_length=n)
+            q = f.query(e, cq.device, database=args.db)
+            t = min(x.runtime_in_sec for x in q if x.n_elements == n)
+            print(f"{mod:24s} {next(iter(e.arg_to_dtype.values()))!s:8s} E={n:8d}  best={best}  {t * 1e3:.4f} ms", flush=True)
+
+
+if __name__ == "__main__":
+    main()
