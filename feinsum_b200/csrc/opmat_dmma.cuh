@@ -263,6 +263,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   // operator tables are staged while the first TMA loads are in flight
   // main operator fragments, column tiles in pairs so that one LDS.128 feeds two of them:
   // sB[((kt*2 + p)*32 + lane)*2 + h] = D[r][8(2p+h)+g][4jq+t]
+  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
   for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
     const int h = idx & 1, ln = (idx >> 1) & 31, p = (idx >> 6) & 1, kt = idx >> 7;
     const int g = ln >> 2, t = ln & 3, jq = kt / 3, r = kt - 3 * jq;
@@ -270,6 +271,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
     sB[idx] = (j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
   }
   // left-over dofs: sL[(kt*4 + t)*4 + d] = D[r][32+d][4jq+t]
+  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
   for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
     const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
     const int jq = kt / 3, r = kt - 3 * jq, j = 4 * jq + t;
@@ -552,6 +554,7 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
   if (cur < nchunks && !dbg_noload) grad_issue(s, bar, &maps, Jg, ug, cur, E, tma, lane);
   // operator tables are staged while the first TMA loads are in flight
   // sB[(tile*KT + kt)*32 + lane]: B[k = t][n = c], c = lane>>2 -> value v = 2*tile + (c&1) of lane c>>1
+  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
   for (int idx = threadIdx.x; idx < L::B_DOUBLES; idx += blockDim.x) {
     const int ln = idx & 31, kt = (idx >> 5) % L::KT, tile = (idx >> 5) / L::KT;
     const int c = ln >> 2, t = ln & 3;
@@ -684,12 +687,14 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
     lift_issue<FE>(s, bar, &maps.in[0], &maps.jac, Jg, static_cast<const double*>(rows.field[0]), cur, E, tma, lane);
   // operator tables are staged while the first TMA loads are in flight
   // sB[(kt*4 + nt)*32 + lane] = Op(f, 8nt+g, j),  k = 4kt+t = 15 f + j
+  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
   for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
     const int ln = idx & 31, nt = (idx >> 5) % kNT, kt = (idx >> 5) / kNT;
     const int g = ln >> 2, t = ln & 3, k = 4 * kt + t, f = k / 15, j = k - 15 * f;
     const int i = 8 * nt + g;
     sB[idx] = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
   }
+  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
   for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
     const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
     const int k = 4 * kt + t, f = k / 15, j = k - 15 * f, i = 32 + d;
@@ -1009,8 +1014,10 @@ static int launch_dmma(int kind, const void* jac, const void* op, const OpmatRow
   }
 }
 
-// wave_3d_p4: placeholder sequencing of the three dmma kernels until the
-// single-launch kernel lands (tracked in DESIGN.md)
+// wave_3d_p4: the three kernels back to back on the caller's stream -- the structure of the reference, whose
+// single loopy translation unit is split into three device kernels (examples/wave_3d_p4_auto.py:36-56).  A
+// single persistent kernel was sized and rejected (shared memory for 6 instead of 10-12
+// warps per SM; the einsums share only J, 72 of 5 456 B per element).
 static int launch_wave3d_dmma(const fnsm_wave_args* a, long long E, const fnsm_cfg* cfg,
                               const DevInfo& di, cudaStream_t st) {
   OpmatRows r1{}; r1.field[0] = a->v; r1.out[0] = a->div_out;

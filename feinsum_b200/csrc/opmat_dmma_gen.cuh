@@ -53,6 +53,7 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
   double* stage = s + L::SLOT_DOUBLES;
 
   // operator table in fragment order: sB[(kt*NT + nt)*32 + lane] = B[k = (kt, t)][n = 8 nt + g]
+  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
   for (int idx = threadIdx.x; idx < L::B_DOUBLES; idx += blockDim.x) {
     const int ln = idx & 31, nt = (idx >> 5) % L::NT, kt = (idx >> 5) / L::NT;
     const int gg = ln >> 2, tt = ln & 3, n = 8 * nt + gg;

@@ -154,6 +154,7 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
   __syncwarp();
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   // operator table [hi | pad | lo], UMMA K-major canonical layout, zero padded (k >= 35, n >= 105)
+  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
   for (int idx = threadIdx.x; idx < L::NP * L::K; idx += blockDim.x) {
     const int n = idx / L::K, k = idx - n * L::K;
     const int i = n / 3, r = n - 3 * i;
@@ -346,6 +347,7 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
   __syncwarp();
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   // operator table [hi | pad | lo]: row n = dof i, k = 15 f + j
+  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
   for (int idx = threadIdx.x; idx < L::NP * L::K; idx += blockDim.x) {
     const int n = idx / L::K, k = idx - n * L::K;
     const int f = k / NFD, j = k - NFD * f;
@@ -530,6 +532,7 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
   __syncwarp();
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   // operator table [hi | lo]: row n = dof i, k = 40 r + j
+  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
   for (int idx = threadIdx.x; idx < L::N * L::NCHUNK * L::KC; idx += blockDim.x) {
     const int n = idx / (L::NCHUNK * L::KC), k = idx - n * (L::NCHUNK * L::KC);
     const int r = k / L::KC, j = k - r * L::KC;

@@ -59,6 +59,7 @@ __device__ __forceinline__ void flush_plain32(float* __restrict__ dst, const flo
 // per lane and fragment -> a single conflict-free LDS.128 feeds the three MMAs of a product
 template <class F>
 __device__ __forceinline__ void fill_b_table(uint4* tab, int n_frag, F value_at /* (frag, lane, half) */) {
+  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
   for (int idx = threadIdx.x; idx < n_frag * 32; idx += blockDim.x) {
     const int frag = idx >> 5, ln = idx & 31;
     uint4 v;
