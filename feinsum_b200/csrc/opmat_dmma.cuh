@@ -110,6 +110,11 @@ __device__ __forceinline__ double2 lds_v2(uint32_t addr) {
 __device__ __forceinline__ void dfma_inplace(double& c, double a, double b) {
   asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(c) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 lanes sharing g
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -255,7 +260,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   const double* sJ = s + 3 * L::U_SLAB;
   const long long nchunks = (E + kCH - 1) / kCH;
   const WorkQueue wq{work_ctr, nchunks};
-  const int g = lane >> 2, t = lane & 3;
+  const int g = lane >> 2, t = lane & 3, tpad = t < 3 ? t : 2;
 
   const bool tma = flags & kFlagTma, dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
   long long cur = wq.take(lane), nxt = wq.take(lane);
@@ -296,13 +301,12 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
       for (int xr = 0; xr < 9; ++xr) Jr[xr] = sJ[xr * kCH + el];
 #pragma unroll
       for (int jq = 0; jq < 9; ++jq) {
+        // k-slot j = 35 (jq = 8, t = 3) is padding: its operator entries are zero, so the lane reads j = 34 of its
+        // own element there (finite whenever the element's data is) instead of paying a select per value
+        const int j = jq == 8 ? 32 + tpad : 4 * jq + t;
         double ux[3];
 #pragma unroll
-        for (int x = 0; x < 3; ++x) {
-          double v = s[x * L::U_SLAB + el * 35 + 4 * jq + t];
-          if (jq == 8 && t == 3) v = 0.0;           // j = 35 is padding
-          ux[x] = v;
-        }
+        for (int x = 0; x < 3; ++x) ux[x] = s[x * L::U_SLAB + el * 35 + j];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
           a[m][3 * jq + r] = fma(Jr[6 + r], ux[2], fma(Jr[3 + r], ux[1], Jr[r] * ux[0]));
