@@ -228,6 +228,7 @@ __device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps
   }
 }
 
+// (grad was tried with direct stores as well: its (x, element, dof-triple) store pattern costs 3.5x in time.)
 // STAGED: results leave through a shared-memory stage + one TMA store (4.4 KB per warp); otherwise
 // straight from the accumulator fragments with 8-byte streaming stores, which frees the shared
 // memory for two more warps (19 KB per warp staged -> 10 warps, 14.6 KB direct -> 12 warps)
@@ -551,7 +552,7 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
   const double* sJ = s + L::U_SLAB;
   const long long nchunks = (E + kCH - 1) / kCH;
   const WorkQueue wq{work_ctr, nchunks};
-  const int g = lane >> 2, t = lane & 3;
+  const int g = lane >> 2, t = lane & 3, tpad = t < 3 ? t : 2;
 
   const bool tma = flags & kFlagTma, dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
   long long cur = wq.take(lane), nxt = wq.take(lane);
@@ -575,11 +576,8 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
     for (int m = 0; m < kME; ++m) {
       const int el = chunk_el(g, m);
 #pragma unroll
-      for (int kt = 0; kt < L::KT; ++kt) {
-        double v = s[el * 35 + 4 * kt + t];
-        if (kt == 8 && t == 3) v = 0.0;
-        a[m][kt] = v;
-      }
+      for (int kt = 0; kt < L::KT; ++kt)       // k-slot j = 35 is padding (zero operator entries): reads j = 34
+        a[m][kt] = s[el * 35 + (kt == 8 ? 32 + tpad : 4 * kt + t)];
 #pragma unroll
       for (int xr = 0; xr < 9; ++xr) Jr[m][xr] = sJ[xr * kCH + el];
     }
