@@ -31,7 +31,7 @@ int opmat_cfg_space(int kernel_id, fnsm_cfg_range* out, int cap) {
   set_range(&tmp[n++], "variant", 0, 3, 1, 0);
   set_range(&tmp[n++], "tile_e", 8, 64, 8, 16);        // simt: elements per CTA tile
   set_range(&tmp[n++], "ctas_per_sm", 1, 8, 1, 0);     // persistent grid size
-  set_range(&tmp[n++], "threads", 128, 448, 32, 0);   // dmma: 32 * warps per persistent CTA (4, 8..12, 14)
+  set_range(&tmp[n++], "threads", 128, 512, 32, 0);   // dmma: 32 * warps per persistent CTA (4, 8..12, 14, 16)
   set_range(&tmp[n++], "stages", 0, 1, 1, 1);          // dmma: shared-memory slots per warp
   for (int i = 0; i < n && i < cap; ++i) out[i] = tmp[i];
   return n;
