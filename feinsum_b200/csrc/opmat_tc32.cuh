@@ -14,7 +14,7 @@
 //   One MMA per k-step computes  A_hi x [B_hi | pad | B_lo]  (N = 240: columns 0..111 main,
 //   128..239 corr), a second one (N = 112) adds  A_lo x B_hi  into the corr columns.
 //
-// Structure: one persistent CTA per SM with two independent GROUPS of 4 warps.  A group owns two TMA
+// Structure: one persistent CTA per SM with two (p = 4) to four (lower orders) independent GROUPS of 4 warps.  A group owns two TMA
 // slots (double buffered element rows), an A_hi/A_lo operand buffer that doubles as the output
 // stage, 224 TMEM columns, and walks its tiles serially:
 //     wait slot -> split rows into the UMMA canonical K-major layout (no swizzle) -> elected thread
@@ -111,8 +111,11 @@ struct GradTC {
   static constexpr int N = tc_pad(3 * ND, 16);          // columns n = 3 i + r (112, 105 used)
   static constexpr int NP = tc_pad(N, 32);              // column pitch main -> corr (TMEM) = row pitch hi -> lo (table)
   static constexpr int NB = NP + N;                     // rows of the operator table: [hi | pad | lo] = 240
-  static constexpr int WPG = 8, GT = 32 * WPG, NH = WPG / 4;     // warps / threads per group, threads per row
-  static constexpr int GROUPS = 2, THREADS = GROUPS * GT;
+  // groups per CTA: the tiles of the lower orders are small (6-40 KB), so their fixed latencies (TMA, MMA
+  // completion, group barriers) are covered by four independent groups instead of two
+  static constexpr int GROUPS = ND <= 20 ? 4 : 2;
+  static constexpr int WPG = GROUPS == 2 ? 8 : 4, GT = 32 * WPG, NH = WPG / 4;   // warps / threads per group, threads per row
+  static constexpr int THREADS = GROUPS * GT;
   static constexpr int B_LBO = NB * 16;                 // operator table: addr(n, k) = (k/4) B_LBO + 16 n + 4 (k%4)
   static constexpr int A_LBO = TM * 16;                 // A operand:      addr(e, k) = (k/4) A_LBO + 16 e + 4 (k%4)
   static constexpr int B_BYTES = (K / 4) * B_LBO;       // 35 840
@@ -122,9 +125,10 @@ struct GradTC {
   static constexpr int STAGE_BYTES = tc_pad(tc_max(OUT_BYTES, 2 * A_BYTES), 128);   // the A operand aliases the stage
   static constexpr int NQ = (ND + 7) / 8;               // epilogue passes of 8 dofs (24 columns)
   static constexpr int GROUP_BYTES = 2 * SLOT_BYTES + STAGE_BYTES;
-  static constexpr int TMEM_COLS_PER_GROUP = 256;       // 240 used
-  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 128;
-  static_assert(NB <= TMEM_COLS_PER_GROUP && 24 * NQ + NP <= TMEM_COLS_PER_GROUP, "TMEM budget");
+  static constexpr int TMEM_COLS_PER_GROUP = 512 / GROUPS;      // 256 (240 used)
+  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 256;   // + mbarriers, TMEM base
+  static_assert(NB <= TMEM_COLS_PER_GROUP && NP + tc_pad(3 * ND, 8) <= TMEM_COLS_PER_GROUP, "TMEM budget");
+  static_assert(SMEM <= 227 * 1024, "shared-memory budget");
   static_assert(SLOT_BYTES % 128 == 0, "TMA destination alignment");
 };
 
@@ -265,6 +269,7 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
       float m[24], c[24];
 #pragma unroll
       for (int p = 0; p < 3; ++p) {
+        if (24 * q + 8 * p >= 3 * ND) continue;          // nothing useful (and possibly nothing allocated) there
         tmem_ld8(tmem_lane + 24 * q + 8 * p, reinterpret_cast<float(&)[8]>(m[8 * p]));
         tmem_ld8(tmem_lane + L::NP + 24 * q + 8 * p, reinterpret_cast<float(&)[8]>(c[8 * p]));
       }
@@ -298,7 +303,7 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
 // out_k[e,i] = sum_{f,j} Op(f,i,j) Jf(e,f) v_k[f,e,j]:  K = (f, j) = 60 -> 64, N = 35 -> 48.
 // The A operand (Jf v, split hi / lo) is written straight into TMEM by the thread that owns the row
 // (tcgen05.st) and consumed from there (tcgen05.mma with A in TMEM): no shared-memory round trip.
-// TMEM columns of a group: [0,48) main, [64,112) corr, [128,192) A_hi, [192,256) A_lo.
+// TMEM columns of a group (p = 4): [0,48) main, [64,112) corr, [112,176) A_hi, [176,240) A_lo.
 // Work item = (tile, field); the face Jacobian of a tile is fetched once for its fields.
 // ND volume dofs, NFD dofs per face (p = 1..4 tets: 4/3, 10/6, 20/10, 35/15), 4 faces
 template <int ND, int NFD>
@@ -307,7 +312,7 @@ struct LiftTC {
   static constexpr int K = tc_pad(4 * NFD, 8), KS = K / 8;                      // 64, 8
   static constexpr int N = tc_pad(ND, 16), NP = tc_pad(N, 32), NB = NP + N;     // 48, 64; table rows [hi | pad | lo] = 112
   static constexpr int WPG = 4, GT = 32 * WPG, NH = WPG / 4;
-  static constexpr int GROUPS = 2, THREADS = GROUPS * GT;
+  static constexpr int GROUPS = ND <= 10 ? 4 : (ND <= 20 ? 3 : 2), THREADS = GROUPS * GT;   // see GradTC
   static constexpr int B_LBO = NB * 16;
   static constexpr int B_BYTES = (K / 4) * B_LBO;       // 28 672
   static constexpr int V_SLAB = TM * NFD;               // floats per face
@@ -315,10 +320,11 @@ struct LiftTC {
   static constexpr int STAGE_BYTES = TM * ND * 4;       // 17 920
   static constexpr int NQ = (ND + 7) / 8;
   static constexpr int GROUP_BYTES = 2 * SLOT_BYTES + STAGE_BYTES;
-  static constexpr int TMEM_COLS_PER_GROUP = 256, A_HI_COL = 128, A_LO_COL = 192;
-  static_assert(NB <= A_HI_COL && K <= 64 && K % 8 == 0, "TMEM budget");
+  static constexpr int TMEM_COLS_PER_GROUP = GROUPS == 2 ? 256 : (GROUPS == 3 ? 160 : 128);
+  static constexpr int A_HI_COL = tc_pad(NB, 16), A_LO_COL = A_HI_COL + K;      // 112 -> [0,112) D, [112,176) A_hi, [176,240) A_lo
+  static_assert(A_LO_COL + K <= TMEM_COLS_PER_GROUP && K % 8 == 0, "TMEM budget");
   static_assert(SLOT_BYTES % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA alignment");
-  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 128;
+  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 256;   // + mbarriers, TMEM base
 };
 
 struct LiftTCMaps { CUtensorMap in[8]; CUtensorMap out[8]; };
@@ -492,7 +498,7 @@ struct DivTC {
   static constexpr int KC = tc_pad(ND, 8), KS_C = KC / 8, NCHUNK = 3;   // per chunk: padded length (40), k-steps
   static constexpr int N = tc_pad(ND, 16), NB = 2 * N;  // 48; operator table rows [hi | lo] = 96
   static constexpr int WPG = 4, GT = 32 * WPG, NH = WPG / 4;
-  static constexpr int GROUPS = 2, THREADS = GROUPS * GT;
+  static constexpr int GROUPS = ND <= 10 ? 4 : (ND <= 20 ? 3 : 2), THREADS = GROUPS * GT;   // see GradTC
   static constexpr int B_LBO = NB * 16;                 // 1536
   static constexpr int B_BYTES = NCHUNK * (KC / 4) * B_LBO;   // 46 080
   static constexpr int U_SLAB = TM * ND;                // floats per x
@@ -500,10 +506,11 @@ struct DivTC {
   static constexpr int STAGE_BYTES = TM * ND * 4;       // 17 920
   static constexpr int NQ = (ND + 7) / 8;
   static constexpr int GROUP_BYTES = SLOT_BYTES + STAGE_BYTES;
-  static constexpr int TMEM_COLS_PER_GROUP = 256, A_COL = NB, A_BUF = 2 * KC, A_LO = KC;
+  static constexpr int TMEM_COLS_PER_GROUP = GROUPS == 2 ? 256 : (GROUPS == 3 ? 160 : 128);
+  static constexpr int A_COL = NB, A_BUF = 2 * KC, A_LO = KC;
   static_assert(A_COL + 2 * A_BUF <= TMEM_COLS_PER_GROUP, "TMEM budget");
   static_assert(SLOT_BYTES % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA alignment");
-  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 128;
+  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 256;   // + mbarriers, TMEM base
 };
 
 struct DivTCMaps { CUtensorMap in, out; };
