@@ -113,7 +113,7 @@ struct GradTC {
   static constexpr int NB = NP + N;                     // rows of the operator table: [hi | pad | lo] = 240
   // groups per CTA: the tiles of the lower orders are small (6-40 KB), so their fixed latencies (TMA, MMA
   // completion, group barriers) are covered by four independent groups instead of two
-  static constexpr int GROUPS = ND <= 20 ? 4 : 2;
+  static constexpr int GROUPS = ND <= 4 ? 8 : (ND <= 20 ? 4 : 2);
   static constexpr int WPG = GROUPS == 2 ? 8 : 4, GT = 32 * WPG, NH = WPG / 4;   // warps / threads per group, threads per row
   static constexpr int THREADS = GROUPS * GT;
   static constexpr int B_LBO = NB * 16;                 // operator table: addr(n, k) = (k/4) B_LBO + 16 n + 4 (k%4)
@@ -126,7 +126,7 @@ struct GradTC {
   static constexpr int NQ = (ND + 7) / 8;               // epilogue passes of 8 dofs (24 columns)
   static constexpr int GROUP_BYTES = 2 * SLOT_BYTES + STAGE_BYTES;
   static constexpr int TMEM_COLS_PER_GROUP = 512 / GROUPS;      // 256 (240 used)
-  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 256;   // + mbarriers, TMEM base
+  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 512;   // + mbarriers, TMEM base
   static_assert(NB <= TMEM_COLS_PER_GROUP && NP + tc_pad(3 * ND, 8) <= TMEM_COLS_PER_GROUP, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "shared-memory budget");
   static_assert(SLOT_BYTES % 128 == 0, "TMA destination alignment");
@@ -312,7 +312,7 @@ struct LiftTC {
   static constexpr int K = tc_pad(4 * NFD, 8), KS = K / 8;                      // 64, 8
   static constexpr int N = tc_pad(ND, 16), NP = tc_pad(N, 32), NB = NP + N;     // 48, 64; table rows [hi | pad | lo] = 112
   static constexpr int WPG = 4, GT = 32 * WPG, NH = WPG / 4;
-  static constexpr int GROUPS = ND <= 10 ? 4 : (ND <= 20 ? 3 : 2), THREADS = GROUPS * GT;   // see GradTC
+  static constexpr int GROUPS = ND <= 4 ? 6 : (ND <= 10 ? 4 : (ND <= 20 ? 3 : 2)), THREADS = GROUPS * GT;   // see GradTC
   static constexpr int B_LBO = NB * 16;
   static constexpr int B_BYTES = (K / 4) * B_LBO;       // 28 672
   static constexpr int V_SLAB = TM * NFD;               // floats per face
@@ -320,11 +320,11 @@ struct LiftTC {
   static constexpr int STAGE_BYTES = TM * ND * 4;       // 17 920
   static constexpr int NQ = (ND + 7) / 8;
   static constexpr int GROUP_BYTES = 2 * SLOT_BYTES + STAGE_BYTES;
-  static constexpr int TMEM_COLS_PER_GROUP = GROUPS == 2 ? 256 : (GROUPS == 3 ? 160 : 128);
+  static constexpr int TMEM_COLS_PER_GROUP = GROUPS == 2 ? 256 : (GROUPS == 3 ? 160 : (GROUPS == 4 ? 128 : 80));
   static constexpr int A_HI_COL = tc_pad(NB, 16), A_LO_COL = A_HI_COL + K;      // 112 -> [0,112) D, [112,176) A_hi, [176,240) A_lo
   static_assert(A_LO_COL + K <= TMEM_COLS_PER_GROUP && K % 8 == 0, "TMEM budget");
   static_assert(SLOT_BYTES % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA alignment");
-  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 256;   // + mbarriers, TMEM base
+  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 512;   // + mbarriers, TMEM base
 };
 
 struct LiftTCMaps { CUtensorMap in[8]; CUtensorMap out[8]; };
@@ -498,7 +498,7 @@ struct DivTC {
   static constexpr int KC = tc_pad(ND, 8), KS_C = KC / 8, NCHUNK = 3;   // per chunk: padded length (40), k-steps
   static constexpr int N = tc_pad(ND, 16), NB = 2 * N;  // 48; operator table rows [hi | lo] = 96
   static constexpr int WPG = 4, GT = 32 * WPG, NH = WPG / 4;
-  static constexpr int GROUPS = ND <= 10 ? 4 : (ND <= 20 ? 3 : 2), THREADS = GROUPS * GT;   // see GradTC
+  static constexpr int GROUPS = ND <= 4 ? 8 : (ND <= 10 ? 4 : (ND <= 20 ? 3 : 2)), THREADS = GROUPS * GT;   // see GradTC
   static constexpr int B_LBO = NB * 16;                 // 1536
   static constexpr int B_BYTES = NCHUNK * (KC / 4) * B_LBO;   // 46 080
   static constexpr int U_SLAB = TM * ND;                // floats per x
@@ -506,11 +506,11 @@ struct DivTC {
   static constexpr int STAGE_BYTES = TM * ND * 4;       // 17 920
   static constexpr int NQ = (ND + 7) / 8;
   static constexpr int GROUP_BYTES = SLOT_BYTES + STAGE_BYTES;
-  static constexpr int TMEM_COLS_PER_GROUP = GROUPS == 2 ? 256 : (GROUPS == 3 ? 160 : 128);
+  static constexpr int TMEM_COLS_PER_GROUP = GROUPS == 2 ? 256 : (GROUPS == 3 ? 160 : (GROUPS == 4 ? 128 : 64));
   static constexpr int A_COL = NB, A_BUF = 2 * KC, A_LO = KC;
   static_assert(A_COL + 2 * A_BUF <= TMEM_COLS_PER_GROUP, "TMEM budget");
   static_assert(SLOT_BYTES % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA alignment");
-  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 256;   // + mbarriers, TMEM base
+  static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 512;   // + mbarriers, TMEM base
 };
 
 struct DivTCMaps { CUtensorMap in, out; };
