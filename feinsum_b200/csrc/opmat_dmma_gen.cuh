@@ -22,6 +22,8 @@ constexpr int gen_pad(int v, int m) { return (v + m - 1) / m * m; }
 template <int KIND, int ND, int NFD>
 struct GenLayout {
   static constexpr bool GRAD = KIND == FNSM_OP_GRAD, DIV = KIND == FNSM_OP_DIV, LIFT = !GRAD && !DIV;
+  // element tiles (of 8) per chunk: the small orders take 32 elements per item to amortise the per-item instructions
+  static constexpr int ME = ND <= 4 ? 4 : 2, CH = 8 * ME;   // (p = 2 with 32 elements: 254 registers, grad 82 -> 77 %)
   static constexpr int JQ = (ND + 3) / 4;                                   // j-quads of a dof row
   // contraction: grad k = j; div k-tile = (jq, r), k-in-tile t <-> j = 4 jq + t; lift k = NFD f + j
   static constexpr int KT = GRAD ? JQ : (DIV ? 3 * JQ : gen_pad(4 * NFD, 4) / 4);
@@ -30,10 +32,10 @@ struct GenLayout {
   static constexpr int PITCH = 8 * NT + 2;                                  // stage row pitch (doubles), skewed
   static constexpr int B_DOUBLES = KT * NT * 32;
   // slot: element data of one chunk, then the Jacobian entries [xr][el] (grad / div: 9, lift: 4)
-  static constexpr int IN_DOUBLES = GRAD ? kCH * ND : (DIV ? 3 * kCH * ND : 4 * kCH * NFD);
-  static constexpr int J_DOUBLES = (LIFT ? 4 : 9) * kCH;
+  static constexpr int IN_DOUBLES = GRAD ? CH * ND : (DIV ? 3 * CH * ND : 4 * CH * NFD);
+  static constexpr int J_DOUBLES = (LIFT ? 4 : 9) * CH;
   static constexpr int SLOT_DOUBLES = IN_DOUBLES + J_DOUBLES;
-  static constexpr int STAGE_DOUBLES = kCH * PITCH;
+  static constexpr int STAGE_DOUBLES = CH * PITCH;
   static constexpr int WARP_DOUBLES = SLOT_DOUBLES + STAGE_DOUBLES;
   static constexpr int NW = 8;
   static constexpr size_t SMEM = 8 * ((size_t)B_DOUBLES + (size_t)NW * WARP_DOUBLES);
@@ -72,7 +74,7 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
   }
   __syncthreads();
 
-  const long long nchunks = (E + kCH - 1) / kCH;
+  const long long nchunks = (E + L::CH - 1) / L::CH;
   const long long wstride = (long long)gridDim.x * L::NW;
   const long long chunk0 = (long long)blockIdx.x * L::NW + warp;
   const long long my_chunks = chunk0 < nchunks ? (nchunks - chunk0 + wstride - 1) / wstride : 0;
@@ -86,13 +88,13 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
   auto fetch = [&](long long item) {
     const long long chunk = chunk0 + (item / nrows) * wstride;
     const int row = (int)(item % nrows);
-    const long long e0 = chunk * kCH;
-    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+    const long long e0 = chunk * L::CH;
+    const int ne = (int)((E - e0 < L::CH) ? (E - e0) : L::CH);
     const double* __restrict__ in = static_cast<const double*>(rows.field[row]);
     constexpr int W = L::GRAD || L::DIV ? ND : NFD;        // row length of one slab
 #pragma unroll
     for (int q = 0; q < NIN; ++q) {
-      const int k = lane + 32 * q, slab = k / (kCH * W), kk = k - slab * (kCH * W);
+      const int k = lane + 32 * q, slab = k / (L::CH * W), kk = k - slab * (L::CH * W);
       rin[q] = kk < ne * W ? ldg_stream(in + ((long long)slab * E + e0) * W + kk) : 0.0;
     }
     if (row == 0) {
@@ -103,7 +105,7 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
         if (L::LIFT && !FE) {
           if (k < L::J_DOUBLES && (k >> 2) < ne) v = ldg_stream(Jg + e0 * 4 + k);       // J(E, 4): contiguous
         } else {
-          const int xr = k / kCH, el = k - xr * kCH;
+          const int xr = k / L::CH, el = k - xr * L::CH;
           if (k < L::J_DOUBLES && el < ne) v = ldg_stream(Jg + (long long)xr * E + e0 + el);
         }
         rj[q] = v;
@@ -114,8 +116,8 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
   for (long long item = 0; item < nitems; ++item) {
     const long long chunk = chunk0 + (item / nrows) * wstride;
     const int row = (int)(item % nrows);
-    const long long e0 = chunk * kCH;
-    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+    const long long e0 = chunk * L::CH;
+    const int ne = (int)((E - e0 < L::CH) ? (E - e0) : L::CH);
     double* __restrict__ out = static_cast<double*>(rows.out[row]);
     {
       // ---- registers -> slot (the previous item's stores have been issued; its slot reads are done) ----
@@ -126,7 +128,7 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
         for (int q = 0; q < NJR; ++q) {
           const int k = lane + 32 * q;
           if (k < L::J_DOUBLES) {
-            if (L::LIFT && !FE) sJ[(k & 3) * kCH + (k >> 2)] = rj[q];                    // transposed to [f][el]
+            if (L::LIFT && !FE) sJ[(k & 3) * L::CH + (k >> 2)] = rj[q];                    // transposed to [f][el]
             else sJ[k] = rj[q];
           }
         }
@@ -134,9 +136,9 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
       if (item + 1 < nitems) fetch(item + 1);
       __syncwarp();
       // ---- A fragments: lane (g, t) holds rows el = g + 8 m, k = (kt, t) ----
-      double a[kME][L::KT];
+      double a[L::ME][L::KT];
 #pragma unroll
-      for (int m = 0; m < kME; ++m) {
+      for (int m = 0; m < L::ME; ++m) {
         const int el = g + 8 * m;
         if (L::GRAD) {
 #pragma unroll
@@ -147,13 +149,13 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
         } else if (L::DIV) {
           double Jr[9];
 #pragma unroll
-          for (int xr = 0; xr < 9; ++xr) Jr[xr] = sJ[xr * kCH + el];
+          for (int xr = 0; xr < 9; ++xr) Jr[xr] = sJ[xr * L::CH + el];
 #pragma unroll
           for (int jq = 0; jq < L::JQ; ++jq) {
             const int j = 4 * jq + t;
             double ux[3];
 #pragma unroll
-            for (int x = 0; x < 3; ++x) ux[x] = j < ND ? s[(x * kCH + el) * ND + j] : 0.0;
+            for (int x = 0; x < 3; ++x) ux[x] = j < ND ? s[(x * L::CH + el) * ND + j] : 0.0;
 #pragma unroll
             for (int r = 0; r < 3; ++r)
               a[m][3 * jq + r] = fma(Jr[6 + r], ux[2], fma(Jr[3 + r], ux[1], Jr[r] * ux[0]));
@@ -162,7 +164,7 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
 #pragma unroll
           for (int kt = 0; kt < L::KT; ++kt) {
             const int k = 4 * kt + t, f = k / NFD, j = k - NFD * f;
-            a[m][kt] = k < 4 * NFD ? sJ[f * kCH + el] * s[(f * kCH + el) * NFD + j] : 0.0;
+            a[m][kt] = k < 4 * NFD ? sJ[f * L::CH + el] * s[(f * L::CH + el) * NFD + j] : 0.0;
           }
         }
       }
@@ -170,9 +172,9 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
 #pragma unroll
       for (int nt0 = 0; nt0 < L::NT; nt0 += 4) {          // at most 4 column tiles (16 accumulators) at a time
         constexpr int NTG = 4;
-        double acc[kME][NTG][2];
+        double acc[L::ME][NTG][2];
 #pragma unroll
-        for (int m = 0; m < kME; ++m)
+        for (int m = 0; m < L::ME; ++m)
 #pragma unroll
           for (int q = 0; q < NTG; ++q) { acc[m][q][0] = 0.0; acc[m][q][1] = 0.0; }
 #pragma unroll
@@ -182,12 +184,12 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
             if (nt0 + q < L::NT) {
               const double b = sB[(kt * L::NT + nt0 + q) * 32 + lane];
 #pragma unroll
-              for (int m = 0; m < kME; ++m) dmma884(acc[m][q], a[m][kt], b);
+              for (int m = 0; m < L::ME; ++m) dmma884(acc[m][q], a[m][kt], b);
             }
           }
         }
 #pragma unroll
-        for (int m = 0; m < kME; ++m)
+        for (int m = 0; m < L::ME; ++m)
 #pragma unroll
           for (int q = 0; q < NTG; ++q)
             if (nt0 + q < L::NT)
@@ -203,7 +205,7 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
 #pragma unroll
           for (int x = 0; x < 3; ++x)
             stg_stream(out + ((long long)x * E + e0) * ND + idx,
-                       fma(sJ[(3 * x + 2) * kCH + el], T[2], fma(sJ[(3 * x + 1) * kCH + el], T[1], sJ[(3 * x) * kCH + el] * T[0])));
+                       fma(sJ[(3 * x + 2) * L::CH + el], T[2], fma(sJ[(3 * x + 1) * L::CH + el], T[1], sJ[(3 * x) * L::CH + el] * T[0])));
         } else {
           stg_stream(out + e0 * ND + idx, stage[el * L::PITCH + i]);
         }
@@ -234,7 +236,7 @@ static int launch_dmma_gen_k(const void* jac, const void* op, const OpmatRows& r
     occ_cache[dev & 63].store(occ, std::memory_order_relaxed);
   }
   if (cfg && cfg->ctas_per_sm > 0 && cfg->ctas_per_sm < occ) occ = cfg->ctas_per_sm;
-  const long long nchunks = (E + kCH - 1) / kCH;
+  const long long nchunks = (E + L::CH - 1) / L::CH;
   const long long need = (nchunks + L::NW - 1) / L::NW;
   long long grid = (long long)occ * di.sms;
   if (grid > need) grid = need;
