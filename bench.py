@@ -51,6 +51,12 @@ WORKLOADS = {
     "wave_p4": ("wave_3d_p4 operator: div(v) + grad(u) + 4-field lift in one call, fp64", 4_000_000),
     "wave_p4_f32": ("wave_3d_p4 operator: div(v) + grad(u) + 4-field lift in one call, fp32", 4_000_000),
 }
+# lower-order tets: p = 1..3 -> (volume dofs, face dofs)
+ORDERS = {1: (4, 3), 2: (10, 6), 3: (20, 10), 4: (35, 15)}
+for _p in (1, 2, 3):
+    for _k, _sub in (("div", "xre,rij,xej->ei"), ("grad", "xre,rij,ej->xei"), ("lift", "ifj,fe,fej->ei b=4")):
+        WORKLOADS[f"{_k}_p{_p}"] = (f"DG {_k} {_sub} p={_p} tets fp64", 4_000_000)
+        WORKLOADS[f"{_k}_p{_p}_f32"] = (f"DG {_k} {_sub} p={_p} tets fp32", 4_000_000)
 
 
 def build_einsum(name: str):
@@ -58,17 +64,19 @@ def build_einsum(name: str):
 
     dt = "float32" if name.endswith("_f32") else "float64"
     base = name.replace("_f32", "")
-    if base == "div_p4":
-        return f.einsum("xre,rij,xej->ei", f.array("J", (3, 3, "E"), dt),
-                        f.array("D", (3, 35, 35), dt), f.array("u", (3, "E", 35), dt))
-    if base == "grad_p4":
-        return f.einsum("xre,rij,ej->xei", f.array("J", (3, 3, "E"), dt),
-                        f.array("D", (3, 35, 35), dt), f.array("u", ("E", 35), dt))
-    if base == "lift_p4":
+    kind, _, order = base.partition("_p")
+    if kind in ("div", "grad", "lift") and order in ("1", "2", "3", "4"):
+        nd, nfd = ORDERS[int(order)]
+        if kind == "div":
+            return f.einsum("xre,rij,xej->ei", f.array("J", (3, 3, "E"), dt),
+                            f.array("D", (3, nd, nd), dt), f.array("u", (3, "E", nd), dt))
+        if kind == "grad":
+            return f.einsum("xre,rij,ej->xei", f.array("J", (3, 3, "E"), dt),
+                            f.array("D", (3, nd, nd), dt), f.array("u", ("E", nd), dt))
         return f.batched_einsum(
             "ifj,fe,fej->ei",
-            [[f.array("L", (35, 4, 15), dt), f.array("Jface", (4, "E"), dt),
-              f.array(f"F_{k}", (4, "E", 15), dt)] for k in range(4)])
+            [[f.array("L", (nd, 4, nfd), dt), f.array("Jface", (4, "E"), dt),
+              f.array(f"F_{k}", (4, "E", nfd), dt)] for k in range(4)])
     if base == "tp_p7":
         return f.einsum("eabc,ia->eibc", f.array("A", ("E", 8, 8, 8), dt), f.array("M", (8, 8), dt))
     if base == "wave_p4":
