@@ -14,14 +14,19 @@
 //   One MMA per k-step computes  A_hi x [B_hi | pad | B_lo]  (N = 240: columns 0..111 main,
 //   128..239 corr), a second one (N = 112) adds  A_lo x B_hi  into the corr columns.
 //
-// Structure: one persistent CTA per SM with two (p = 4) to four (lower orders) independent GROUPS of 4 warps.  A group owns two TMA
-// slots (double buffered element rows), an A_hi/A_lo operand buffer that doubles as the output
-// stage, 224 TMEM columns, and walks its tiles serially:
-//     wait slot -> split rows into the UMMA canonical K-major layout (no swizzle) -> elected thread
-//     issues the MMAs + tcgen05.commit and re-arms the slot with the TMA load two tiles ahead ->
-//     wait commit -> tcgen05.ld, apply J, stage -> one TMA tensor store.
-// While one group waits on its MMAs / stores the other converts or drains, so the SM stays busy
-// without any cross-group synchronisation.
+// Structure: one persistent CTA per SM with several independent GROUPS of warps -- two at p = 4, three to
+// eight at the lower orders, whose tiles are small enough (6-40 KB) that the fixed latencies of a tile
+// dominate.  A group owns its TMA slot(s), its share of the 512 TMEM columns, an output stage (grad: the
+// A_hi / A_lo operand buffer aliases it) and its mbarriers, and walks its tiles serially:
+//     wait slot -> split rows (grad: into the UMMA canonical K-major layout in shared memory; div / lift:
+//     straight into TMEM) -> elected thread issues the MMAs + tcgen05.commit and re-arms the slot with
+//     the next TMA load -> wait commit -> tcgen05.ld, apply J (grad), stage -> one TMA tensor store.
+// While one group waits on its loads / MMAs / stores the others convert or drain, so the SM stays busy
+// without any cross-group synchronisation.  A group is 4 warps (warp w owns TMEM lanes 32 (w & 3) .. +31,
+// thread = element row) or, for grad at p = 4, 8 warps: warps w and w + 4 share a lane quadrant and split
+// the k-columns of the conversion and the dof columns of the epilogue (that pays where conversion and
+// epilogue are long -- grad 90 -> 99 % -- and costs where a tile already has several barriers -- div
+// 94 -> 90 %, lift 95 -> 93 %).
 #pragma once
 #include "opmat_tf32.cuh"
 
@@ -95,10 +100,6 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
 }
 
 // ================================================================ GRAD =====
-// A group is WPG (4 or 8) warps: warps w and w + 4 of a group share the TMEM lane quadrant w & 3 (rows
-// 32 (w & 3) .. +31) and split the k-columns of the conversion and the dof columns of the epilogue.
-// (WPG = 8 pays where conversion and epilogue are long -- grad: 94 % vs 90 % -- and costs where the
-// tile already has several barriers -- div: 89 % vs 94 %.)
 
 constexpr int tc_pad(int v, int m) { return (v + m - 1) / m * m; }
 constexpr int tc_max(int a, int b) { return a > b ? a : b; }
