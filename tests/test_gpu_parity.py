@@ -146,6 +146,36 @@ def test_fp32_tensor_path_accuracy_margin(cq, variant):
             assert rel < 3e-6, (builder.__name__, k, rel)
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("builder", [E.grad, E.div, E.lift_fe, E.lift_ef])
+def test_misaligned_operands_take_the_plain_path(cq, builder, dtype):
+    """Operands that are views at an odd offset into a larger allocation (bases not 16-byte aligned)
+    rule out every TMA tensor map: auto must fall back (DMMA plain-load path / mma.sync kernel) and still
+    match the oracle; outputs are views at an odd offset as well."""
+    import torch
+
+    e = builder(dtype=dtype)
+    n = 1000
+    ins = np_oracle.generate_input_arrays(e, n, 11)
+    tdt = torch.float64 if dtype == "float64" else torch.float32
+    dev = {}
+    for k, v in ins.items():
+        flat = torch.zeros(v.size + 3, dtype=tdt, device=cq.torch_device)
+        view = flat[1:1 + v.size].view(v.shape)          # base + one element: 8 / 4 bytes off a 16-byte boundary
+        view.copy_(torch.from_numpy(np.ascontiguousarray(v)))
+        assert view.data_ptr() % 16 != 0 and view.is_contiguous()
+        dev[k] = view
+    out_shape = tuple(int(d) if isinstance(d, (int, np.integer)) else n for d in e.shape)
+    for name in e.output_names:
+        flat = torch.zeros(int(np.prod(out_shape)) + 3, dtype=tdt, device=cq.torch_device)
+        dev[name] = flat[1:1 + int(np.prod(out_shape))].view(out_shape)
+    evt, outs = generate_cuda(e).executor(cq)(cq, **dev)
+    evt.wait()
+    got = {k: v.cpu().numpy() for k, v in outs.items()}
+    ref = (np_oracle.reference_outputs_fp64 if dtype == "float32" else np_oracle.reference_outputs)(e, ins)
+    np_oracle.assert_matches(got, ref, north_star=True)
+
+
 @pytest.mark.parametrize("n", [1, 100])
 def test_grad_batched(cq, n):
     check(E.grad_batched(3), n, cq)
