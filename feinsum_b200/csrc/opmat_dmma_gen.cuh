@@ -42,7 +42,9 @@ struct GenLayout {
 };
 
 template <int KIND, int ND, int NFD>
-__global__ void __launch_bounds__(256)
+// two CTAs per SM (<= 128 registers) wherever that does not spill: div at p = 3 holds 60 A-fragment and 60 prefetch
+// registers and runs as one CTA per SM
+__global__ void __launch_bounds__(256, (KIND == FNSM_OP_DIV && ND >= 20) ? 1 : 2)
 k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, const __grid_constant__ OpmatRows rows,
                  int nrows, long long E) {
   using L = GenLayout<KIND, ND, NFD>;
