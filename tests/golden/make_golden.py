@@ -215,6 +215,34 @@ VALID = {
         "args": [[_arr("J", (3, 3, "E"), "float32"), _arr("D", (3, 35, 35), "float32"),
                   _arr("u", ("E", 35), "float32")]],
     },
+    # lower-order tets (reference tuning/impls/ifj_fe_fej_to_ei_v3.py:602: ndof 4/10/20, nfacedof 3/6/10)
+    "grad_p2": {
+        "subscripts": "xre,rij,ej->xei",
+        "args": [[_arr("J", (3, 3, "E")), _arr("D", (3, 10, 10)), _arr("u", ("E", 10))]],
+    },
+    "div_p3": {
+        "subscripts": "xre,rij,xej->ei",
+        "args": [[_arr("J", (3, 3, "E")), _arr("D", (3, 20, 20)), _arr("u", (3, "E", 20))]],
+    },
+    "lift_fe_p1_b4": {
+        "subscripts": "ifj,fe,fej->ei",
+        "args": [
+            [_arr("L", (4, 4, 3)), _arr("Jface", (4, "E")), _arr(f"F_{k}", (4, "E", 3))]
+            for k in range(4)
+        ],
+    },
+    "lift_p3_b4": {
+        "subscripts": "ef,fij,fej->ei",
+        "args": [
+            [_arr("J", ("E", 4)), _arr("R", (4, 20, 10)), _arr(f"v{k}", (4, "E", 10))]
+            for k in range(4)
+        ],
+    },
+    "div_p2_f32": {
+        "subscripts": "xre,rij,xej->ei",
+        "args": [[_arr("J", (3, 3, "E"), "float32"), _arr("D", (3, 10, 10), "float32"),
+                  _arr("u", (3, "E", 10), "float32")]],
+    },
 }
 
 INVALID = {
@@ -289,6 +317,7 @@ NUMERIC = {
     "grad_p4": 6, "div_p4": 6, "lift_p4_b4": 6, "lift_fe_p4_b4": 6,
     "tensor_product_p7": 4, "div_components": 5, "face_mass_se": 5,
     "matvec_f32": 1, "matvec_f32_long": 9, "diag_access": 1, "grad_p4_f32": 6,
+    "grad_p2": 20, "div_p3": 20, "lift_fe_p1_b4": 20, "lift_p3_b4": 20, "div_p2_f32": 20,
 }
 
 

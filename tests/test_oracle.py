@@ -15,6 +15,7 @@ CASES = [
     "grad_p4", "div_p4", "lift_p4_b4", "lift_fe_p4_b4", "tensor_product_p7",
     "div_components", "face_mass_se", "matvec_f32", "matvec_f32_long", "diag_access",
     "grad_p4_f32",
+    "grad_p2", "div_p3", "lift_fe_p1_b4", "lift_p3_b4", "div_p2_f32",
 ]
 
 
