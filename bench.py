@@ -1,25 +1,35 @@
 #!/usr/bin/env python
 """
 bench.py -- BASELINE.json metric: GFLOP/s & HBM GB/s (% of B200 roofline) per
-DG einsum, beside the CPU restatement of the reference path.
+DG einsum at 1/2/4/8 GPUs, beside the CPU restatement of the reference path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME]
+                    [--impl reference] [--scaling weak|strong] [--no-suite]
 
-One *step* = one execution of the einsum over the whole element batch
-(BASELINE config 2 by default: DG divergence ``xre,rij,xej->ei``, p = 4 tets,
-fp64, E = 4 000 000 elements per GPU; 4.77 GB of operands >> 126 MB L2, so
-every step streams from HBM -- no L2 flush needed).  N > 1: launched under
-torchrun, one rank per GPU, element axis sharded (every rank owns E elements:
-weak scaling), no collective on the data path; time = max over ranks.
+Headline (``value``, ``roofline``, ``e2e``, ``cpu_baseline``): one *step* = one
+execution of ``--workload`` over the whole element batch (default BASELINE
+config 2: DG divergence ``xre,rij,xej->ei``, p = 4 tets, fp64, E = 4 000 000
+elements per GPU; 4.77 GB of operands >> 126 MB L2, so every step streams from
+HBM).  N > 1: launched under torchrun, one rank per GPU, element axis sharded,
+no collective on the data path; time = max over ranks.
 
-Printed JSON (one line, rank 0):  value = whole-job GFLOP/s with operands
-resident in HBM; ``e2e`` = same metric through the host-buffer API
-(``HostExecutor``: pinned numpy in, numpy out, H2D/D2H inside the timed
-region); ``roofline`` = the kernel against the measured FP64 peak
-(``fnsm_b200_measure_peak`` in this run -- MEASURED_PEAKS.json only carries
-HBM and bf16) and against the measured HBM copy bandwidth; ``cpu_baseline`` =
-the oracle's C/OpenMP restatement of the reference's generated loop nest on the
-host cores (loopy -> pocl cannot run in this image).
+``workloads``: unless ``--no-suite``, the same line carries every other
+BASELINE config timed the same way (fewer steps): grad p4 at E = 100 000
+(config 1; L2-resident and with L2 flushed between launches) and 4 M, div / lift
+at 100 000, lift p4 (config 3), the wave_3d_p4 operator in fp64 and fp32
+(config 4), tensor-product p7 (config 5: 4 M elements per GPU = 32 M at N = 8)
+and the three fp32 DG kernels -- each with ms/step, GFLOP/s, GB/s and its
+roofline fraction against the burst and the sustained peaks.
+``strong``: div p4, wave_3d_p4 and tensor-product at a FIXED total of
+16 000 000 elements split over the N ranks.
+
+``e2e`` = the headline metric through the host-buffer API (``HostExecutor``:
+pinned numpy in, numpy out, H2D/D2H inside the timed region), with the raw
+pinned-copy time of the same bytes on the same ranks as ``pcie_floor_ms``.
+``cpu_baseline`` / ``--impl reference`` = the oracle's C/OpenMP restatement of
+the reference's generated loop nest on the host cores (loopy -> pocl cannot run
+in this image); the GPU arm runs the reference arm's code in a subprocess so
+both legs follow one policy.
 """
 
 from __future__ import annotations
@@ -27,6 +37,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -38,25 +49,39 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 METRIC = "GFLOP/s per DG einsum (opt_einsum-path flops), with HBM GB/s and % of B200 roofline"
+L2_BYTES = 126e6
+STRONG_TOTAL = 16_000_000
 
 WORKLOADS = {
-    # name: (builder name in this file, default E per GPU, description)
-    "div_p4": ("DG divergence xre,rij,xej->ei p=4 tets fp64", 4_000_000),
-    "grad_p4": ("DG gradient xre,rij,ej->xei p=4 tets fp64", 4_000_000),
-    "lift_p4": ("DG face-mass lift ifj,fe,fej->ei b=4 p=4 tets fp64", 4_000_000),
-    "tp_p7": ("tensor-product eabc,ia->eibc p=7 hexes fp64", 4_000_000),
-    "div_p4_f32": ("DG divergence xre,rij,xej->ei p=4 tets fp32", 4_000_000),
-    "grad_p4_f32": ("DG gradient xre,rij,ej->xei p=4 tets fp32", 4_000_000),
-    "lift_p4_f32": ("DG face-mass lift ifj,fe,fej->ei b=4 p=4 tets fp32", 4_000_000),
-    "wave_p4": ("wave_3d_p4 operator: div(v) + grad(u) + 4-field lift in one call, fp64", 4_000_000),
-    "wave_p4_f32": ("wave_3d_p4 operator: div(v) + grad(u) + 4-field lift in one call, fp32", 4_000_000),
+    # name: (description, default elements per GPU, BASELINE.json config it belongs to)
+    "div_p4": ("DG divergence xre,rij,xej->ei p=4 tets fp64", 4_000_000, "configs[1]"),
+    "grad_p4": ("DG gradient xre,rij,ej->xei p=4 tets fp64", 4_000_000, "configs[0] einsum at the configs[1] size"),
+    "lift_p4": ("DG face-mass lift ifj,fe,fej->ei b=4 p=4 tets fp64", 4_000_000, "configs[2]"),
+    "tp_p7": ("tensor-product eabc,ia->eibc p=7 hexes fp64", 4_000_000, "configs[4] (4 M elements per GPU)"),
+    "div_p4_f32": ("DG divergence xre,rij,xej->ei p=4 tets fp32", 4_000_000, "configs[1] einsum in fp32"),
+    "grad_p4_f32": ("DG gradient xre,rij,ej->xei p=4 tets fp32", 4_000_000, "configs[0] einsum in fp32"),
+    "lift_p4_f32": ("DG face-mass lift ifj,fe,fej->ei b=4 p=4 tets fp32", 4_000_000, "configs[2] einsum in fp32"),
+    "wave_p4": ("wave_3d_p4 operator: div(v) + grad(u) + 4-field lift in one call, fp64", 4_000_000, "configs[3] fp64"),
+    "wave_p4_f32": ("wave_3d_p4 operator: div(v) + grad(u) + 4-field lift in one call, fp32", 4_000_000, "configs[3] fp32"),
+    "hexd_p7": ("fused hex derivative eabc,ia->eibc + eabc,ib->eaic + eabc,ic->eabi p=7 fp64 (A read once)",
+                4_000_000, "SURVEY 8(f3)"),
 }
 # lower-order tets: p = 1..3 -> (volume dofs, face dofs)
 ORDERS = {1: (4, 3), 2: (10, 6), 3: (20, 10), 4: (35, 15)}
 for _p in (1, 2, 3):
     for _k, _sub in (("div", "xre,rij,xej->ei"), ("grad", "xre,rij,ej->xei"), ("lift", "ifj,fe,fej->ei b=4")):
-        WORKLOADS[f"{_k}_p{_p}"] = (f"DG {_k} {_sub} p={_p} tets fp64", 4_000_000)
-        WORKLOADS[f"{_k}_p{_p}_f32"] = (f"DG {_k} {_sub} p={_p} tets fp32", 4_000_000)
+        WORKLOADS[f"{_k}_p{_p}"] = (f"DG {_k} {_sub} p={_p} tets fp64", 4_000_000, "SURVEY 8(f3)")
+        WORKLOADS[f"{_k}_p{_p}_f32"] = (f"DG {_k} {_sub} p={_p} tets fp32", 4_000_000, "SURVEY 8(f3)")
+
+# what the default command times besides the headline: (workload, elements per GPU or None = default, flush L2?)
+SUITE = [
+    ("grad_p4", 100_000, False), ("grad_p4", 100_000, True), ("div_p4", 100_000, False),
+    ("lift_p4", 100_000, False),
+    ("grad_p4", None, False), ("lift_p4", None, False), ("wave_p4", None, False),
+    ("wave_p4_f32", None, False), ("tp_p7", None, False),
+    ("grad_p4_f32", None, False), ("div_p4_f32", None, False), ("lift_p4_f32", None, False),
+]
+STRONG_SUITE = ["div_p4", "wave_p4", "tp_p7"]
 
 
 def build_einsum(name: str):
@@ -79,13 +104,77 @@ def build_einsum(name: str):
               f.array(f"F_{k}", (4, "E", nfd), dt)] for k in range(4)])
     if base == "tp_p7":
         return f.einsum("eabc,ia->eibc", f.array("A", ("E", 8, 8, 8), dt), f.array("M", (8, 8), dt))
-    if base == "wave_p4":
-        return None          # three einsums behind one call: see feinsum_b200/wave3d.py
+    if base in ("wave_p4", "hexd_p7"):
+        return None          # several einsums behind one call: feinsum_b200/wave3d.py, hexderiv.py
     raise SystemExit(f"unknown workload {name}")
 
 
 def concrete(shape, n):
     return tuple(int(d) if isinstance(d, (int, np.integer)) else n for d in shape)
+
+
+def dtype_of(name: str) -> str:
+    return "f32" if name.endswith("_f32") else "f64"
+
+
+class Work:
+    """Per-element work model + program of one workload (no GPU needed to construct)."""
+
+    def __init__(self, name: str, params: dict | None = None):
+        from feinsum_b200 import measure
+
+        self.name = name
+        self.descr, self.default_e, self.baseline_cfg = WORKLOADS[name]
+        self.dtype = dtype_of(name)
+        self.np_dtype = np.float32 if self.dtype == "f32" else np.float64
+        self.params = dict(params or {})
+        self.einsum = build_einsum(name)
+        base = name.replace("_f32", "")
+        if base == "wave_p4":
+            from feinsum_b200 import wave3d
+
+            self.flops = float(wave3d.FLOPS_PER_ELEMENT)
+            self.bytes = float(wave3d.BYTES_PER_ELEMENT[np.dtype(self.np_dtype)])
+            self.program = wave3d.Wave3DProgram(self.np_dtype, **self.params)
+            self.cpu_einsums = list(wave3d.wave3d_einsums(self.np_dtype).values())
+        elif base == "hexd_p7":
+            from feinsum_b200 import hexderiv
+
+            self.flops = float(hexderiv.FLOPS_PER_ELEMENT)
+            self.bytes = float(hexderiv.BYTES_PER_ELEMENT[np.dtype(self.np_dtype)])
+            self.program = hexderiv.HexDerivProgram(self.np_dtype, **self.params)
+            self.cpu_einsums = list(hexderiv.hexderiv_einsums(self.np_dtype).values())
+        else:
+            from feinsum_b200.codegen import generate_cuda
+
+            self.flops = sum(measure.get_flops_per_dtype(self.einsum, 1_000_000).values()) / 1e6
+            self.bytes = (measure.get_footprint_bytes(self.einsum, 2_000_000)
+                          - measure.get_footprint_bytes(self.einsum, 1_000_000)) / 1e6
+            self.program = generate_cuda(self.einsum)
+            if self.params:
+                self.program = self.program.with_params(**self.params)
+            self.cpu_einsums = [self.einsum]
+
+    def shapes(self, E: int):
+        if self.einsum is None:
+            spec = self.program.host_spec()
+            return ({n: concrete(s, E) for n, s in sorted(spec.in_shapes.items())},
+                    {n: concrete(s, E) for n, s in spec.out_shapes.items()})
+        es = self.einsum
+        return ({n: concrete(s, E) for n, s in sorted(es.arg_to_shape.items())},
+                {n: concrete(es.shape, E) for n in es.output_names})
+
+    def l2_policy(self, E: int, flush: bool) -> str:
+        ws = self.bytes * E
+        if flush:
+            return (f"working set {ws / 1e6:.0f} MB <= L2: L2 flushed between timed launches "
+                    "(256 MB buffer rewritten; each launch timed by its own event pair)")
+        if ws > 4 * L2_BYTES:
+            return f"operands >> L2 ({ws / 1e9:.2f} GB vs 126 MB): inputs larger than L2, no flush"
+        if ws > L2_BYTES:
+            return f"working set {ws / 1e6:.0f} MB vs 126 MB L2: partially cached, launched back to back WITHOUT flush"
+        return (f"working set {ws / 1e6:.0f} MB <= 126 MB L2: launched back to back WITHOUT flush "
+                "(L2-resident, the regime of the reference's database size E = 100 000)")
 
 
 # ------------------------------------------------------------------ clocks --
@@ -149,9 +238,10 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------- cpu legs ---
-def cpu_reference_leg(einsum, flops_per_elem: float, sample_e: int, steps: int, warmup: int):
-    """Times the oracle's C/OpenMP loop nest (trivial schedule, as generate_loopy +
-    identity transform emits it) on all host cores.  Returns (GFLOP/s, cores, ms/step)."""
+def cpu_reference_leg(einsums, flops_per_elem: float, sample_e: int, steps: int, warmup: int):
+    """Times the oracle's C/OpenMP loop nests (trivial schedule, as generate_loopy +
+    identity transform emits them; one nest per einsum of the workload, run one after the
+    other) on all host cores.  Returns (GFLOP/s, cores, ms/step)."""
     from oracle import cgen, np_oracle
 
     cores = len(os.sched_getaffinity(0))
@@ -163,30 +253,74 @@ def cpu_reference_leg(einsum, flops_per_elem: float, sample_e: int, steps: int, 
         ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)   # if the runtime was initialised already
     except OSError:
         pass
-    kern = cgen.CKernel(einsum)
-    ins = np_oracle.generate_input_arrays(einsum, sample_e, 0)
-    outs = [np.empty(s, dtype=np.result_type(*[a.dtype for a in row]))
-            for s, row in zip(kern.out_shapes(sample_e), einsum.args)]
+    legs = []
+    for es in einsums:
+        kern = cgen.CKernel(es)
+        ins = np_oracle.generate_input_arrays(es, sample_e, 0)
+        outs = [np.empty(s, dtype=np.result_type(*[a.dtype for a in row]))
+                for s, row in zip(kern.out_shapes(sample_e), es.args)]
+        legs.append((kern, ins, outs))
+
+    def step():
+        for kern, ins, outs in legs:
+            kern(sample_e, ins, outs)
+
     for _ in range(max(1, warmup)):
-        kern(sample_e, ins, outs)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        kern(sample_e, ins, outs)
+        step()
     dt = (time.perf_counter() - t0) / steps
     return flops_per_elem * sample_e / dt * 1e-9, cores, dt * 1e3
 
 
-def cpu_reference_leg_wave(dtype: str, sample_e: int, steps: int, warmup: int):
-    """CPU port of the wave operator = its three loop nests run one after the other."""
-    from feinsum_b200 import measure, wave3d
+def reference_sample_elements(work: Work, E: int) -> int:
+    """Elements per step of the CPU arm: the labelled E when inputs + outputs fit comfortably in
+    host RAM and a step stays within a few seconds, else a bounded sample (stated in the line)."""
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 8e9
+    n = E
+    while n > 100_000 and (work.bytes * n * 2.5 > avail or work.flops * n > 4e10):
+        n //= 2
+    return n
 
-    secs = 0.0
-    cores = 1
-    for e in wave3d.wave3d_einsums("float32" if dtype == "f32" else "float64").values():
-        fl = sum(measure.get_flops_per_dtype(e, 1_000_000).values()) / 1e6
-        gf, cores, _ = cpu_reference_leg(e, fl, sample_e, steps, warmup)
-        secs += fl * sample_e / (gf * 1e9)
-    return wave3d.FLOPS_PER_ELEMENT * sample_e / secs * 1e-9, cores, secs * 1e3
+
+def reference_arm(work: Work, E: int, n_gpus: int, steps: int, warmup: int, sample_e: int | None) -> dict:
+    sample_e = sample_e or reference_sample_elements(work, E)
+    gf, cores, ms = cpu_reference_leg(work.cpu_einsums, work.flops, sample_e, steps, warmup)
+    config = make_config(work, E, max(1, n_gpus), "weak", False)
+    config["reference_sample_elements_per_step"] = sample_e
+    return {
+        "impl": "reference", "metric": METRIC,
+        "value": gf, "unit": "GFLOP/s", "n_gpus": n_gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": work.dtype, "data": "synthetic",
+        "config": config,
+        "cpu_baseline": {
+            "value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "port",
+            "sample": (f"{sample_e} elements per step"
+                       + ("" if sample_e == E else f" (bounded sample of the labelled {E})")
+                       + ": C/OpenMP restatement of the loop nest generate_loopy emits "
+                         "(trivial schedule, -O3 -ffast-math -fopenmp); the reference's "
+                         "loopy->pocl path cannot run in this image"),
+        },
+        "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def make_config(work: Work, E: int, world: int, scaling: str, flush: bool) -> dict:
+    return {
+        "workload": f"{work.descr}, {E} elements per GPU (BASELINE {work.baseline_cfg})",
+        "elements_per_gpu": E,
+        "elements_total": E * world,
+        "flops_per_element": work.flops,
+        "bytes_per_element": work.bytes,
+        "l2_policy": work.l2_policy(E, flush),
+        "parallelism": f"element axis sharded over {world} GPU(s) ({scaling} scaling), no collective",
+    }
 
 
 def profiled_traffic(workload: str):
@@ -209,6 +343,252 @@ def profiled_traffic(workload: str):
     return tot, os.path.relpath(files[-1], ROOT)
 
 
+# ------------------------------------------------------------------ GPU arm --
+class Bench:
+    """Everything the GPU arm shares between workloads: queue, peaks, barrier, L2 flusher."""
+
+    def __init__(self, rank: int, world: int, local_rank: int):
+        import torch
+
+        import feinsum_b200 as f
+        from feinsum_b200 import _cabi
+        from feinsum_b200.data import device_info
+
+        self.torch, self.cabi = torch, _cabi
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        self.dist = None
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            import torch.distributed as dist_mod
+
+            self.dist = dist_mod
+            self.dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        self.cq = f.CudaQueue(local_rank)
+        self.dev = self.cq.torch_device
+        # measured peaks of this board in this run: burst (micro-kernel of a few ms) and sustained
+        # (after ~0.7 s of load the board sits at its power cap and the SM clock drops)
+        self.peak = {}
+        for dt, codes in (("f64", (3, 0)), ("f32", (1,))):
+            self.peak[dt] = {
+                "burst": max(_cabi.measure_peak(c) for c in codes),
+                "sustained": max(_cabi.measure_peak(c + 16) for c in codes),
+            }
+            self.peak[dt]["sustained"] = min(self.peak[dt]["sustained"], self.peak[dt]["burst"])
+        self.hbm_peak = device_info.DEV_TO_PEAK_BW.get("NVIDIA B200", 6561.6)
+        self.hbm_src = "MEASURED_PEAKS.json" if device_info._hbm is not None else "fallback table"
+        self.hbm_here = _cabi.measure_peak(2)      # this library's own streaming-copy micro-kernel
+        self._flush_buf = None
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.dist is None:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def flush_l2(self):
+        torch = self.torch
+        if self._flush_buf is None:
+            self._flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)
+        with torch.cuda.stream(self.cq.torch_stream):
+            self._flush_buf.fill_(1)
+
+    # ------------------------------------------------------------------
+    def setup(self, work: Work, E: int):
+        torch = self.torch
+        gen = torch.Generator(device=self.dev).manual_seed(1234 + self.rank)
+        tdt = torch.float32 if work.dtype == "f32" else torch.float64
+        in_shapes, out_shapes = work.shapes(E)
+        arrays = {n: torch.rand(s, dtype=tdt, device=self.dev, generator=gen) for n, s in in_shapes.items()}
+        outs = {n: torch.zeros(s, dtype=tdt, device=self.dev) for n, s in out_shapes.items()}
+        ex = work.program.executor(self.cq)
+        return ex, arrays, outs
+
+    def time_steps(self, ex, arrays, outs, steps: int, warmup: int, flush: bool, sample_clocks: bool):
+        """(ms per step on this rank, launches per step, clocks summary)."""
+        torch, cq = self.torch, self.cq
+        for _ in range(warmup):
+            ex(cq, **arrays, **outs)
+        self.barrier()
+        launches0 = self.cabi.launch_count()
+        clocks = ClockSampler(self.local_rank) if sample_clocks else None
+        if clocks is not None:
+            clocks.__enter__()
+        if flush:
+            pairs = []
+            for _ in range(steps):
+                self.flush_l2()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(cq.torch_stream)
+                ex(cq, **arrays, **outs)
+                b.record(cq.torch_stream)
+                pairs.append((a, b))
+            torch.cuda.synchronize()
+            ms_total = sum(a.elapsed_time(b) for a, b in pairs)
+        else:
+            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record(cq.torch_stream)
+            for _ in range(steps):
+                ex(cq, **arrays, **outs)
+            stop.record(cq.torch_stream)
+            stop.synchronize()
+            ms_total = start.elapsed_time(stop)
+        self.barrier()
+        if clocks is not None:
+            clocks.__exit__()
+        launches = self.cabi.launch_count() - launches0
+        return ms_total / steps, launches, (clocks.summary() if clocks is not None else None), ms_total
+
+    def roofline(self, work: Work, E: int, my_ms: float, launches_per_step: int, long_region: bool) -> dict:
+        pk = self.peak[work.dtype]
+        ach_tflops = work.flops * E / (my_ms * 1e-3) * 1e-12
+        ach_gbs = work.bytes * E / (my_ms * 1e-3) * 1e-9
+        t_mem = work.bytes * E / (self.hbm_peak * 1e9)
+
+        def frac_against(peak_fp):
+            return max(work.flops * E / (peak_fp * 1e9), t_mem) / (my_ms * 1e-3)
+
+        kind = "sustained" if long_region else "burst"
+        peak_fp = pk[kind]
+        t_flop = work.flops * E / (peak_fp * 1e9)
+        if t_flop >= t_mem:
+            roof = {"bound": "tensor", "achieved": ach_tflops, "peak": peak_fp * 1e-3,
+                    "unit": "TFLOP/s", "frac": ach_tflops / (peak_fp * 1e-3)}
+        else:
+            roof = {"bound": "hbm", "achieved": ach_gbs, "peak": self.hbm_peak, "unit": "GB/s",
+                    "frac": ach_gbs / self.hbm_peak}
+        engine = "FP64 DMMA/DFMA" if work.dtype == "f64" else "FP32 FFMA2"
+        roof.update({
+            "peak_kind": kind + ("" if not long_region else " (timed region long enough to pull the power cap)"),
+            "frac_burst": frac_against(pk["burst"]), "frac_sustained": frac_against(pk["sustained"]),
+            "peak_burst": pk["burst"] * 1e-3, "peak_sustained": pk["sustained"] * 1e-3,
+            "peak_source": (f"{engine} peaks measured in this run by fnsm_b200_measure_peak (burst: a few ms; "
+                            f"sustained: after 0.7 s of load; MEASURED_PEAKS.json has no {work.dtype} figure); "
+                            f"HBM {self.hbm_peak} GB/s from {self.hbm_src}"),
+            "t_roof_ms": max(t_flop, t_mem) * 1e3, "roofline_frac": max(t_flop, t_mem) / (my_ms * 1e-3),
+            "hbm": {"achieved": ach_gbs, "peak": self.hbm_peak, "frac": ach_gbs / self.hbm_peak,
+                    "streaming_copy_measured_here": self.hbm_here,
+                    "frac_of_best_measured": ach_gbs / max(self.hbm_peak, self.hbm_here)},
+            "fp": {"achieved": ach_tflops, "peak": peak_fp * 1e-3, "frac": ach_tflops / (peak_fp * 1e-3)},
+            "launches_per_step": launches_per_step,
+            "algorithmic_bytes_per_launch": work.bytes * E / launches_per_step,
+            "algorithmic_flops_per_launch": work.flops * E / launches_per_step,
+        })
+        return roof
+
+    def run_workload(self, work: Work, E: int, steps: int, warmup: int, flush: bool = False,
+                     sample_clocks: bool = False) -> dict:
+        """Time one workload on every rank; returns the entry of the JSON line (same fields for the
+        headline and for the suite)."""
+        torch = self.torch
+        ex, arrays, outs = self.setup(work, E)
+        my_ms, launches, clocks, ms_total = self.time_steps(ex, arrays, outs, steps, warmup, flush, sample_clocks)
+        capped = bool(clocks and "sw_power_cap" in clocks["reasons"])
+        roof = self.roofline(work, E, my_ms, max(1, launches // steps), ms_total > 250.0 or capped)
+        ms_step = self.max_over_ranks(my_ms)
+        entry = {
+            "elements_per_gpu": E, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
+            "value": work.flops * E * self.world / (ms_step * 1e-3) * 1e-9, "unit": "GFLOP/s",
+            "gbs": work.bytes * E * self.world / (ms_step * 1e-3) * 1e-9,
+            "dtype": work.dtype, "roofline": roof, "gpu_launches": int(launches),
+            "kernel": work.program.kernel_id, "l2_policy": work.l2_policy(E, flush),
+            "baseline_config": work.baseline_cfg,
+        }
+        if clocks is not None:
+            entry["clocks"] = clocks
+        self._last = (ex, arrays, outs)
+        del ex, arrays, outs
+        return entry
+
+    def release(self):
+        self._last = None
+        self.torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- e2e ---
+    def e2e(self, work: Work, E: int, steps: int) -> dict:
+        """The headline metric through the host-buffer API: pinned numpy in, pinned numpy out, the
+        chunked H2D | kernel | D2H pipeline of HostExecutor inside the timed region; plus the raw
+        pinned-copy time of the same bytes on the same ranks at the same time (the PCIe floor)."""
+        from feinsum_b200.host_exec import HostExecutor, pinned_empty
+
+        torch = self.torch
+        ex, arrays, outs = self._last
+        in_shapes, out_shapes = work.shapes(E)
+        host_in = {}
+        for name, shape in in_shapes.items():
+            h = pinned_empty(shape, work.np_dtype)
+            torch.from_numpy(h).copy_(arrays[name])
+            host_in[name] = h
+        host_out = {n: pinned_empty(s, work.np_dtype) for n, s in out_shapes.items()}
+        hx = HostExecutor(work.program, self.cq)
+        hx(outputs=host_out, **host_in)
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            hx(outputs=host_out, **host_in)
+        self.barrier()
+        dt = self.max_over_ranks((time.perf_counter() - t0) / steps)
+        # spot parity of the host path against the device path
+        for oname in out_shapes:
+            ref = outs[oname][..., :1].cpu().numpy()
+            got = host_out[oname][..., :1]
+            if not np.allclose(got, ref, rtol=1e-12 if work.dtype == "f64" else 1e-5):
+                raise SystemExit("host path and device path disagree")
+        # PCIe floor: the same bytes as plain contiguous pinned copies, H2D and D2H concurrently
+        s_up, s_dn = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)
+        dev_in = {n: torch.empty_like(arrays[n]) for n in arrays}
+
+        def raw():
+            with torch.cuda.stream(s_up):
+                for n in dev_in:
+                    dev_in[n].copy_(torch.from_numpy(host_in[n]), non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                for n in host_out:
+                    torch.from_numpy(host_out[n]).copy_(outs[n], non_blocking=True)
+            s_up.synchronize()
+            s_dn.synchronize()
+
+        raw()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            raw()
+        self.barrier()
+        floor = self.max_over_ranks((time.perf_counter() - t0) / steps)
+        return {"value": work.flops * E * self.world / dt * 1e-9, "unit": "GFLOP/s",
+                "h2d_bytes_per_step": hx.h2d_bytes, "d2h_bytes_per_step": hx.d2h_bytes,
+                "ms_per_step": dt * 1e3, "steps": steps,
+                "pcie_floor_ms": floor * 1e3, "pcie_frac": floor / dt,
+                "h2d_gbs_per_gpu": hx.h2d_bytes / dt * 1e-9, "pcie_floor_h2d_gbs_per_gpu": hx.h2d_bytes / floor * 1e-9,
+                "note": "HostExecutor: pinned numpy in/out, chunked H2D | kernel | D2H on 3 streams; "
+                        "pcie_floor_ms = the same bytes as plain pinned cudaMemcpyAsync (H2D and D2H "
+                        "concurrently, all ranks at once), pcie_frac = floor / e2e time"}
+
+
+def cpu_baseline_subprocess(workload: str, E: int, steps: int = 5, warmup: int = 2) -> dict | None:
+    """Runs this file's reference arm in a fresh process (no torch / CUDA state, all host cores) so the
+    GPU arm's cpu_baseline and `--impl reference` are the same code under the same policy."""
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("OMP_NUM_THREADS", "RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    try:
+        out = subprocess.run(
+            [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload,
+             "--elements", str(E), "--steps", str(steps), "--warmup", str(warmup)],
+            capture_output=True, text=True, env=env, timeout=600, check=True).stdout
+        line = json.loads(out.strip().splitlines()[-1])
+        cpu = line["cpu_baseline"]
+        cpu["sample"] += f"; {line['steps']} steps after {line['warmup']} warm-ups, {line['ms_per_step']:.1f} ms/step"
+        return cpu
+    except Exception as exc:  # noqa: BLE001
+        return {"value": None, "unit": "GFLOP/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                "sample": f"failed: {exc}"}
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,11 +597,16 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="div_p4", choices=sorted(WORKLOADS))
     ap.add_argument("--elements", type=int, default=0, help="elements per GPU (default: workload's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: the headline runs a fixed total of 16 M elements split over the ranks")
     ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 dmma, 2 simt")
     ap.add_argument("--param", action="append", default=[], metavar="K=V",
                     help="launch parameter of the kernel (threads=384, ...); may repeat")
+    ap.add_argument("--flush-l2", action="store_true", help="flush L2 between timed launches of the headline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-suite", action="store_true", help="headline workload only")
+    ap.add_argument("--suite-steps", type=int, default=10)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -230,263 +615,75 @@ def main() -> None:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    from feinsum_b200 import measure
-
-    einsum = build_einsum(args.workload)
-    is_wave = einsum is None
-    descr, default_e = WORKLOADS[args.workload]
-    E = args.elements or default_e
-    dtype = "f32" if args.workload.endswith("_f32") else "f64"
-    if is_wave:
-        from feinsum_b200 import wave3d
-
-        flops_per_elem = float(wave3d.FLOPS_PER_ELEMENT)
-        bytes_per_elem = float(wave3d.BYTES_PER_ELEMENT[np.dtype("float32" if dtype == "f32" else "float64")])
+    params = {k: int(v) for k, v in (kv.split("=") for kv in args.param)}
+    if args.variant > 0:
+        params["variant"] = args.variant
+    work = Work(args.workload, params)
+    if args.scaling == "strong":
+        E = (args.elements or STRONG_TOTAL) // max(world, 1)
     else:
-        flops_per_elem = sum(measure.get_flops_per_dtype(einsum, 1_000_000).values()) / 1e6
-        bytes_per_elem = (measure.get_footprint_bytes(einsum, 2_000_000)
-                          - measure.get_footprint_bytes(einsum, 1_000_000)) / 1e6
-    config = {
-        "workload": f"{descr}, {E} elements per GPU (BASELINE configs[1] family)",
-        "elements_per_gpu": E,
-        "flops_per_element": flops_per_elem,
-        "bytes_per_element": bytes_per_elem,
-        "l2_policy": "operands >> L2 (4.77 GB vs 126 MB): inputs larger than L2, no flush",
-        "parallelism": f"element axis sharded over {max(world, args.gpus)} GPU(s), no collective",
-    }
+        E = args.elements or work.default_e
 
     # ------------------------------------------------------ reference arm ---
     if args.impl == "reference":
         if rank != 0:
             return
-        sample_e = 400_000
-        if is_wave:
-            gf, cores, ms = cpu_reference_leg_wave(dtype, sample_e, args.steps, args.warmup)
-        else:
-            gf, cores, ms = cpu_reference_leg(einsum, flops_per_elem, sample_e, args.steps, args.warmup)
-        line = {
-            "impl": "reference", "metric": METRIC,
-            "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-            "config": config,
-            "cpu_baseline": {
-                "value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "port",
-                "sample": f"{sample_e} elements per step: C/OpenMP restatement of the loop nest "
-                          "generate_loopy emits (trivial schedule, -O3 -ffast-math -fopenmp); "
-                          "the reference's loopy->pocl path cannot run in this image",
-            },
-            "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-        }
-        print(json.dumps(line))
+        print(json.dumps(reference_arm(work, E, args.gpus, args.steps, args.warmup, None)))
         return
 
     # ------------------------------------------------------------ B200 arm --
-    import torch
-
-    import feinsum_b200 as f
-    from feinsum_b200 import _cabi
-    from feinsum_b200.codegen import generate_cuda
-    from feinsum_b200.data import device_info
-    from feinsum_b200.host_exec import HostExecutor, pinned_empty
-    from feinsum_b200 import wave3d
-
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-
-        dist = dist_mod
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    else:
-        torch.cuda.set_device(local_rank)
-    cq = f.CudaQueue(local_rank)
-    dev = cq.torch_device
-
-    params = {k: int(v) for k, v in (kv.split("=") for kv in args.param)}
-    if args.variant > 0:
-        params["variant"] = args.variant
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    tdt = torch.float32 if dtype == "f32" else torch.float64
-    if is_wave:
-        prog = None
-        ex = wave3d.Wave3DExecutor(cq, "float32" if dtype == "f32" else "float64", **params)
-        in_shapes, out_shapes = wave3d.shapes(E)
-        kernel_id = "wave3d"
-    else:
-        prog = generate_cuda(einsum)
-        if params:
-            prog = prog.with_params(**params)
-        ex = prog.executor(cq)
-        in_shapes = {n: concrete(s, E) for n, s in sorted(einsum.arg_to_shape.items())}
-        out_shapes = {n: concrete(einsum.shape, E) for n in einsum.output_names}
-        kernel_id = prog.kernel_id
-    arrays = {n: torch.rand(s, dtype=tdt, device=dev, generator=gen) for n, s in sorted(in_shapes.items())}
-    outs = {n: torch.zeros(s, dtype=tdt, device=dev) for n, s in out_shapes.items()}
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # measured peaks for the roofline (this board, this run): burst figure for a short timed region,
-    # sustained (power-capped) figure when the timed region is long enough to pull the power cap
-    peak_burst = _cabi.measure_peak(3 if dtype == "f64" else 1)   # DMMA fp64 / FFMA2 fp32
-    if dtype == "f64":
-        peak_burst = max(peak_burst, _cabi.measure_peak(0))
-    peak_fp = peak_burst
-    peak_kind = "burst"
-    hbm_peak = device_info.DEV_TO_PEAK_BW.get("NVIDIA B200", 6561.6)
-    hbm_src = "MEASURED_PEAKS.json" if device_info._hbm is not None else "fallback table"
-
-    for _ in range(args.warmup):
-        ex(cq, **arrays, **outs)
-    barrier()
-    launches0 = _cabi.launch_count()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        start.record(cq.torch_stream)
-        for _ in range(args.steps):
-            ex(cq, **arrays, **outs)
-        stop.record(cq.torch_stream)
-        stop.synchronize()
-        barrier()
-    launches = _cabi.launch_count() - launches0
-    ms_total = start.elapsed_time(stop)
-    if ms_total > 250.0 or "sw_power_cap" in clocks.summary()["reasons"]:
-        peak_fp = min(peak_burst, _cabi.measure_peak((3 if dtype == "f64" else 1) + 16))
-        peak_kind = "sustained (power-capped, measured after 0.7 s of load)"
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = flops_per_elem * E * world / (ms_step * 1e-3) * 1e-9
-    gbs = bytes_per_elem * E * world / (ms_step * 1e-3) * 1e-9
-
-    # per-kernel roofline (this rank's kernel)
-    my_ms = ms_total / args.steps
-    launches_per_step = max(1, launches // args.steps)
-    ach_tflops = flops_per_elem * E / (my_ms * 1e-3) * 1e-12
-    ach_gbs = bytes_per_elem * E / (my_ms * 1e-3) * 1e-9
-    t_flop = flops_per_elem * E / (peak_fp * 1e9)
-    t_mem = bytes_per_elem * E / (hbm_peak * 1e9)
-    if t_flop >= t_mem:
-        roof = {"bound": "tensor", "achieved": ach_tflops, "peak": peak_fp * 1e-3,
-                "unit": "TFLOP/s", "frac": ach_tflops / (peak_fp * 1e-3)}
-    else:
-        roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach_gbs / hbm_peak}
-    traffic, traffic_src = (profiled_traffic(args.workload) if E == default_e and not params else (None, None))
-    roof.update({
-        "traffic": traffic, "traffic_source": traffic_src,
-        "peak_kind": peak_kind, "peak_burst": peak_burst * 1e-3,
-        "peak_source": (f"{'FP64 DMMA/DFMA' if dtype == 'f64' else 'FP32 FFMA2'} {peak_kind} peak measured in this run by "
-                        f"fnsm_b200_measure_peak (MEASURED_PEAKS.json has no {dtype} figure); "
-                        f"HBM {hbm_peak} GB/s from {hbm_src}"),
-        "t_roof_ms": max(t_flop, t_mem) * 1e3, "roofline_frac": max(t_flop, t_mem) / (my_ms * 1e-3),
-        "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "frac": ach_gbs / hbm_peak},
-        "fp": {"achieved": ach_tflops, "peak": peak_fp * 1e-3, "frac": ach_tflops / (peak_fp * 1e-3)},
-        "launches_per_step": launches_per_step,
-        "algorithmic_bytes_per_launch": bytes_per_elem * E / launches_per_step,
-        "algorithmic_flops_per_launch": flops_per_elem * E / launches_per_step,
-    })
-
-    # ---------------------------------------------------------------- e2e ---
+    bench = Bench(rank, world, local_rank)
+    custom = bool(params) or bool(args.elements) or args.workload != "div_p4" or args.scaling != "weak"
+    head = bench.run_workload(work, E, args.steps, args.warmup, flush=args.flush_l2, sample_clocks=True)
+    traffic, traffic_src = (profiled_traffic(args.workload)
+                            if E == work.default_e and not params else (None, None))
+    head["roofline"].update({"traffic": traffic, "traffic_source": traffic_src})
     e2e = None
-    if not args.no_e2e and is_wave:
-        # host buffers in, host buffers out, one stream: H2D of all ten operands, the fused
-        # call, D2H of the six results (no chunk pipelining for the three-einsum operator yet)
-        npdt = np.float32 if dtype == "f32" else np.float64
-        host_in = {n: pinned_empty(s, npdt) for n, s in in_shapes.items()}
-        for n in host_in:
-            torch.from_numpy(host_in[n]).copy_(arrays[n])
-        host_out = {n: pinned_empty(s, npdt) for n, s in out_shapes.items()}
-        dev_in = {n: torch.empty_like(a) for n, a in arrays.items()}
+    if not args.no_e2e:
+        e2e = bench.e2e(work, E, max(3, min(args.steps, 5)))
+    bench.release()
 
-        def e2e_step():
-            with torch.cuda.stream(cq.torch_stream):
-                for n in dev_in:
-                    dev_in[n].copy_(torch.from_numpy(host_in[n]), non_blocking=True)
-                ex(cq, **dev_in, **outs)
-                for n in host_out:
-                    torch.from_numpy(host_out[n]).copy_(outs[n], non_blocking=True)
-            cq.finish()
+    suite, strong = {}, {}
+    if not args.no_suite and not custom:
+        for name, n, flush in SUITE:
+            w = Work(name)
+            n = n or w.default_e
+            key = name + (f"@{n}" if n != w.default_e else "") + ("+l2flush" if flush else "")
+            suite[key] = bench.run_workload(w, n, args.suite_steps, 3, flush=flush)
+            bench.release()
+        for name in STRONG_SUITE:
+            w = Work(name)
+            n = STRONG_TOTAL // world
+            ent = bench.run_workload(w, n, args.suite_steps, 3)
+            ent["elements_total"] = n * world
+            strong[name] = ent
+            bench.release()
 
-        e2e_steps = 3
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        barrier()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": flops_per_elem * E * world / dt * 1e-9, "unit": "GFLOP/s",
-               "h2d_bytes_per_step": int(sum(a.nbytes for a in host_in.values())),
-               "d2h_bytes_per_step": int(sum(a.nbytes for a in host_out.values())),
-               "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "note": "pinned numpy in/out; H2D, fused call, D2H in order on one stream"}
-    elif not args.no_e2e:
-        host_in = {}
-        for name, shape in sorted(einsum.arg_to_shape.items()):
-            h = pinned_empty(concrete(shape, E), np.float32 if dtype == "f32" else np.float64)
-            torch.from_numpy(h).copy_(arrays[name])
-            host_in[name] = h
-        host_out = {n: pinned_empty(concrete(einsum.shape, E),
-                                    np.float32 if dtype == "f32" else np.float64)
-                    for n in einsum.output_names}
-        hx = HostExecutor(prog, cq)
-        e2e_steps = max(3, min(args.steps, 5))
-        hx(outputs=host_out, **host_in)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            hx(outputs=host_out, **host_in)
-        barrier()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": flops_per_elem * E * world / dt * 1e-9, "unit": "GFLOP/s",
-               "h2d_bytes_per_step": hx.h2d_bytes, "d2h_bytes_per_step": hx.d2h_bytes,
-               "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "note": "HostExecutor: pinned numpy in/out, chunked H2D | kernel | D2H on 3 streams"}
-        # spot parity of the host path against the device path
-        ref = outs[einsum.output_names[0]][..., :1].cpu().numpy()
-        got = host_out[einsum.output_names[0]][..., :1]
-        if not np.allclose(got, ref, rtol=1e-12 if dtype == "f64" else 1e-5):
-            raise SystemExit("host path and device path disagree")
-
-    # --------------------------------------------------------- cpu baseline -
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample_e = 400_000
-        if is_wave:
-            gf, cores, ms = cpu_reference_leg_wave(dtype, sample_e, 3, 1)
-        else:
-            gf, cores, ms = cpu_reference_leg(einsum, flops_per_elem, sample_e, 3, 1)
-        cpu = {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "port",
-               "sample": f"{sample_e} elements x 3 steps of the C/OpenMP restatement of "
-                         f"generate_loopy's loop nest ({ms:.1f} ms/step)"}
+        cpu = cpu_baseline_subprocess(args.workload, E)
 
     if rank == 0:
         line = {
             "metric": METRIC,
-            "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-            "config": config, "gbs": gbs, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "kernel": kernel_id, "device": cq.device.name,
+            "value": head["value"], "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": work.dtype, "data": "synthetic",
+            "config": make_config(work, E, world, args.scaling, args.flush_l2),
+            "gbs": head["gbs"], "roofline": head["roofline"], "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": head["gpu_launches"] + sum(v["gpu_launches"] for v in suite.values())
+                            + sum(v["gpu_launches"] for v in strong.values()),
+            "gpu_launches_headline": head["gpu_launches"],
+            "clocks": head.get("clocks"), "kernel": head["kernel"], "device": bench.cq.device.name,
         }
+        if suite:
+            line["workloads"] = suite
+        if strong:
+            line["strong"] = {"elements_total": STRONG_TOTAL, "note": "fixed total split over the ranks; "
+                              "speed-up at N = value_N / value_1 of the same entry", **strong}
         print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    if bench.dist is not None:
+        bench.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

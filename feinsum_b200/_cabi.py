@@ -16,7 +16,7 @@ from feinsum_b200.diagnostics import CudaBackendError, InvalidParameterError
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfnsm_b200.so")
 
-FNSM_F64, FNSM_F32 = 0, 1
+FNSM_F64, FNSM_F32, FNSM_I32, FNSM_I64, FNSM_C64, FNSM_C128 = range(6)
 OP_GRAD, OP_DIV, OP_LIFT_EF, OP_LIFT_FE = 0, 1, 2, 3
 K_GENERIC, K_GRAD, K_DIV, K_LIFT, K_WAVE3D, K_TENSOR_PRODUCT = range(6)
 MAX_INDICES, MAX_OPERANDS = 12, 6

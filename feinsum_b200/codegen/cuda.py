@@ -50,6 +50,14 @@ from feinsum_b200.einsum import INT_CLASSES, BatchedEinsum, SizeParam
 from feinsum_b200.make_einsum import parse_subscripts
 
 _DTYPE_CODE = {np.dtype("float64"): _cabi.FNSM_F64, np.dtype("float32"): _cabi.FNSM_F32}
+#: the generic kernel also takes the integer and complex operands the IR accepts
+#: (reference measure.py:63-77 generates them, codegen/loopy.py:258-262 types the result)
+_GENERIC_DTYPE_CODE = {
+    **_DTYPE_CODE,
+    np.dtype("int32"): _cabi.FNSM_I32, np.dtype("int64"): _cabi.FNSM_I64,
+    np.dtype("complex64"): _cabi.FNSM_C64, np.dtype("complex128"): _cabi.FNSM_C128,
+}
+_TORCH_NAMES = ("float64", "float32", "int32", "int64", "complex64", "complex128")
 
 
 # {{{ structural matching (renaming- and operand-order-invariant)
@@ -133,6 +141,36 @@ def _int_extent(einsum: BatchedEinsum, idx: str) -> int | None:
     return int(ext) if isinstance(ext, INT_CLASSES) else None
 
 
+#: shapes with a compiled tensor-core instantiation: tets p = 1..4 (volume dofs, face dofs)
+_TENSOR_ORDERS = {(4, 3), (10, 6), (20, 10), (35, 15)}
+_MAX_SMEM_OPTIN = 232448  # bytes of dynamic shared memory one CTA may opt in to on sm_100
+
+
+def opmat_kernel_available(kid: str, dt: np.dtype[Any], n_outer: int, n_i: int, n_j: int) -> bool:
+    """Does ``fnsm_b200_opmat_batch`` have a kernel for these extents at its default configuration?
+    Mirrors the dispatch in ``csrc/opmat.cu``: the tensor-core kernels cover tets p = 1..4 in 3-D; every
+    other shape runs the simt kernel, which keeps the whole operator plus one element tile in shared
+    memory (``launch_simt``: rejects ``n_outer`` > 4 for grad/div and operators beyond the 227 KB
+    a CTA can opt in to).  Shapes outside that go to the generic kernel instead of failing."""
+    if kid in ("grad", "div"):
+        if n_outer == 3 and n_i == n_j and any(n_i == nd for nd, _ in _TENSOR_ORDERS):
+            return True
+        if n_outer > 4:
+            return False
+    elif n_outer == 4 and (n_i, n_j) in _TENSOR_ORDERS:
+        return True
+    want = (512 + n_i - 1) // n_i
+    tile_e = 16 if want <= 16 else (128 if want >= 128 else (want + 7) // 8 * 8)
+    op = n_outer * n_i * n_j
+    if kid == "grad":
+        elems = op + tile_e * n_j + n_outer * n_outer * tile_e
+    elif kid == "div":
+        elems = op + n_outer * tile_e * n_j + n_outer * n_outer * tile_e
+    else:
+        elems = op + n_outer * tile_e * n_j + n_outer * tile_e
+    return elems * dt.itemsize <= _MAX_SMEM_OPTIN
+
+
 def classify(einsum: BatchedEinsum) -> KernelPlan:
     """Pick the kernel family for *einsum* (never fails: ``generic`` is total
     over what the generic kernel supports; unsupported dtypes raise at
@@ -166,6 +204,9 @@ def classify(einsum: BatchedEinsum) -> KernelPlan:
             else:
                 n_outer = _int_extent(einsum, imap["f"])
             del names
+            n_i, n_j = _int_extent(einsum, imap["i"]), _int_extent(einsum, imap["j"])
+            if not opmat_kernel_available(kid, dt, int(n_outer), int(n_i), int(n_j)):  # type: ignore[arg-type]
+                continue
             return KernelPlan(
                 kid,
                 perm,
@@ -260,9 +301,11 @@ def _torch() -> Any:
 
 def _np_dtype_of(t: Any) -> np.dtype[Any]:
     torch = _torch()
-    return np.dtype(
-        {torch.float64: "float64", torch.float32: "float32"}.get(t.dtype, "object")
-    )
+    return np.dtype({getattr(torch, n): n for n in _TORCH_NAMES}.get(t.dtype, "object"))
+
+
+def _torch_dtype_of(dt: np.dtype[Any]) -> Any:
+    return getattr(_torch(), np.dtype(dt).name)
 
 
 class CudaExecutor:
@@ -283,11 +326,18 @@ class CudaExecutor:
         self.out_dtypes = [np.dtype(d) for d in row_dtypes]
         if self.plan.kernel_id == "generic":
             for row, rd in zip(self.einsum.args, self.out_dtypes):
-                if rd not in _DTYPE_CODE or any(np.dtype(a.dtype) != rd for a in row):
+                if rd not in _GENERIC_DTYPE_CODE or any(np.dtype(a.dtype) != rd for a in row):
                     raise NotImplementedError(
-                        "generic CUDA einsum supports uniform float32/float64 "
-                        f"operands per row, got {[str(a.dtype) for a in row]}"
+                        "generic CUDA einsum supports operands of one dtype per row (float32/64, "
+                        f"int32/64, complex64/128), got {[str(a.dtype) for a in row]}"
                     )
+            if len(set(self.out_dtypes)) != 1:
+                # one launch covers all rows with one scalar type; BatchedEinsum itself only
+                # demands per-name consistency (reference einsum.py:262-272)
+                raise NotImplementedError(
+                    "generic CUDA einsum needs the same dtype in every row of the batch, got "
+                    f"{[str(d) for d in self.out_dtypes]}"
+                )
 
     # -- shape handling --------------------------------------------------
     def _bind_sizes(self, arrays: dict[str, Any]) -> dict[str, int]:
@@ -378,7 +428,7 @@ class CudaExecutor:
         outs: dict[str, Any] = {}
         all_given = True
         for oname, odt in zip(self.output_names, self.out_dtypes):
-            tdt = torch.float64 if odt == np.dtype("float64") else torch.float32
+            tdt = _torch_dtype_of(odt)
             if oname in arrays and arrays[oname] is not None:
                 o = arrays[oname]
                 if tuple(o.shape) != out_shape or o.dtype != tdt or not o.is_contiguous():
@@ -467,7 +517,7 @@ class CudaExecutor:
         }
         desc = _cabi.EinsumDesc()
         desc.n_free, desc.n_sum, desc.n_operands = len(free), len(summed), es.n
-        desc.dtype = _DTYPE_CODE[self.out_dtypes[0]]
+        desc.dtype = _GENERIC_DTYPE_CODE[self.out_dtypes[0]]
         for k, idx in enumerate(order):
             desc.extent[k] = extent[idx]
         # output strides (C order over out_idx_set)

@@ -4,6 +4,7 @@
 #include <mutex>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 
 namespace fnsm {
 
@@ -27,6 +28,12 @@ int device_info(DevInfo* out) {
         cudaDeviceGetAttribute(&di.cc_minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
       cudaGetLastError();
       return FNSM_E_NO_DEVICE;
+    }
+    // test hook: FNSM_B200_MAX_SMS=n makes every persistent kernel size its grid as if the device had n SMs,
+    // so that small inputs walk many work items per warp (sanitizer runs, tests/test_gpu_sanitizer.py)
+    if (const char* cap = std::getenv("FNSM_B200_MAX_SMS")) {
+      const int v = std::atoi(cap);
+      if (v > 0 && v < di.sms) di.sms = v;
     }
     g_dev_cache[dev] = di;
     g_dev_valid[dev] = true;

@@ -10,6 +10,21 @@
 
 namespace fnsm {
 
+// complex scalar for the generic kernel (the IR accepts complex operands, reference measure.py:63-77)
+template <typename R>
+struct Cx {
+  R re, im;
+  __device__ Cx() : re(0), im(0) {}
+  __device__ Cx(int v) : re((R)v), im(0) {}
+  __device__ Cx& operator*=(const Cx& o) {
+    const R r = re * o.re - im * o.im;
+    im = re * o.im + im * o.re;
+    re = r;
+    return *this;
+  }
+  __device__ Cx& operator+=(const Cx& o) { re += o.re; im += o.im; return *this; }
+};
+
 struct GenericRows {
   const void* in[8][FNSM_MAX_OPERANDS];
   void* out[8];
@@ -76,7 +91,7 @@ extern "C" int fnsm_b200_generic_einsum(const fnsm_einsum_desc* desc, int32_t b,
   const int nf = desc->n_free, ns = desc->n_sum, nop = desc->n_operands;
   if (nf < 0 || ns < 0 || nf + ns > FNSM_MAX_INDICES || nop < 1 || nop > FNSM_MAX_OPERANDS)
     return FNSM_E_UNSUPPORTED;
-  if (desc->dtype != FNSM_F64 && desc->dtype != FNSM_F32) return FNSM_E_UNSUPPORTED;
+  if (desc->dtype < FNSM_F64 || desc->dtype > FNSM_C128) return FNSM_E_UNSUPPORTED;
   long long n_out = 1;
   for (int f = 0; f < nf; ++f) {
     if (desc->extent[f] < 0) return FNSM_E_BAD_ARG;
@@ -104,10 +119,14 @@ extern "C" int fnsm_b200_generic_einsum(const fnsm_einsum_desc* desc, int32_t b,
     long long blocks = (work + 255) / 256;
     const long long cap = (long long)di.sms * 16;
     if (blocks > cap) blocks = cap;
-    if (desc->dtype == FNSM_F64)
-      k_generic_einsum<double><<<(unsigned)blocks, 256, 0, st>>>(*desc, rows, nr, n_out);
-    else
-      k_generic_einsum<float><<<(unsigned)blocks, 256, 0, st>>>(*desc, rows, nr, n_out);
+    switch (desc->dtype) {
+      case FNSM_F64: k_generic_einsum<double><<<(unsigned)blocks, 256, 0, st>>>(*desc, rows, nr, n_out); break;
+      case FNSM_F32: k_generic_einsum<float><<<(unsigned)blocks, 256, 0, st>>>(*desc, rows, nr, n_out); break;
+      case FNSM_I32: k_generic_einsum<int><<<(unsigned)blocks, 256, 0, st>>>(*desc, rows, nr, n_out); break;
+      case FNSM_I64: k_generic_einsum<long long><<<(unsigned)blocks, 256, 0, st>>>(*desc, rows, nr, n_out); break;
+      case FNSM_C64: k_generic_einsum<Cx<float>><<<(unsigned)blocks, 256, 0, st>>>(*desc, rows, nr, n_out); break;
+      default: k_generic_einsum<Cx<double>><<<(unsigned)blocks, 256, 0, st>>>(*desc, rows, nr, n_out); break;
+    }
     if (int rc = post_launch()) return rc;
   }
   return FNSM_OK;

@@ -124,6 +124,11 @@ __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 lanes
 
 // lets a kernel launched with programmatic stream serialization behind this one start as SMs free up (launch_k)
 __device__ __forceinline__ void release_dependent_kernels() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Counterpart, executed by every thread right before it exits: a grid that was itself launched with programmatic
+// stream serialization does not complete before the grid ahead of it has completed and flushed its writes, so
+// "this grid is done" keeps implying "everything before it on the stream is done" (events, copies and later
+// kernels order against the LAST kernel only).  No-op for a normally launched grid.
+__device__ __forceinline__ void wait_for_previous_kernels() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // warp index as a value ptxas can prove warp-uniform (keeps TMA operands in uniform registers)
 __device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
@@ -445,6 +450,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
     nxt = wq.resolve(tk);
   }
   if (lane == 0) tma_store_wait_all();
+  wait_for_previous_kernels();
 }
 
 // ================================================================ GRAD =====
@@ -612,6 +618,7 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
     nxt = wq.resolve(tk);
   }
   if (lane == 0) tma_store_wait_all();
+  wait_for_previous_kernels();
 }
 
 // ================================================================ LIFT =====
@@ -806,6 +813,7 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
     fld = nfld;
   }
   if (lane == 0) tma_store_wait_all();
+  wait_for_previous_kernels();
 }
 
 // ------------------------------------------------------------ launchers ----

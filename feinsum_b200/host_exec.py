@@ -14,34 +14,54 @@ Operands whose element axis is not the leading one (``J(3,3,E)``,
 re-packing on the host.  Host arrays should be page-locked
 (:func:`pinned_empty`) -- pageable memory works but serialises the copies.
 
+*program* is a :class:`~feinsum_b200.codegen.cuda.CudaProgram` or anything with
+the same three members (``host_spec()``, ``executor(cq)``), e.g.
+:class:`feinsum_b200.wave3d.Wave3DProgram` -- the three-einsum wave operator
+goes through the same chunk pipeline.
+
 This is the reference-facing path that ``bench.py`` reports as ``e2e``.
 """
 
 from __future__ import annotations
 
 import ctypes as C
+from dataclasses import dataclass
 from typing import Any
 
 import numpy as np
 
 from feinsum_b200 import _cabi
 from feinsum_b200.cl_utils import CudaQueue, as_queue
-from feinsum_b200.codegen.cuda import CudaProgram
-from feinsum_b200.einsum import SizeParam
+from feinsum_b200.einsum import BatchedEinsum, SizeParam
 
 
 def pinned_empty(shape: tuple[int, ...], dtype: Any) -> np.ndarray:
-    """Page-locked host array (numpy view of a pinned torch tensor)."""
+    """Page-locked host array: a numpy view of a pinned torch tensor.  The view's ``base`` chain
+    owns the tensor, so the pinned allocation is released when the last view of it goes away."""
     import torch
 
     tdt = {np.dtype("float64"): torch.float64, np.dtype("float32"): torch.float32}[np.dtype(dtype)]
-    t = torch.empty(shape, dtype=tdt, pin_memory=True)
-    a = t.numpy()
-    _KEEPALIVE[id(a)] = t
-    return a
+    return torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
 
 
-_KEEPALIVE: dict[int, Any] = {}
+@dataclass(frozen=True)
+class HostSpec:
+    """Names, symbolic shapes and dtypes of what crosses the host boundary."""
+
+    in_shapes: dict[str, tuple[Any, ...]]
+    in_dtypes: dict[str, np.dtype[Any]]
+    out_shapes: dict[str, tuple[Any, ...]]
+    out_dtypes: dict[str, np.dtype[Any]]
+
+
+def einsum_host_spec(es: BatchedEinsum) -> HostSpec:
+    return HostSpec(
+        {n: tuple(s) for n, s in es.arg_to_shape.items()},
+        {n: np.dtype(d) for n, d in es.arg_to_dtype.items()},
+        {n: tuple(es.shape) for n in es.output_names},
+        {n: np.dtype(np.result_type(*[a.dtype for a in row]))
+         for n, row in zip(es.output_names, es.args)},
+    )
 
 
 def _long_axis(shape: tuple[Any, ...]) -> int | None:
@@ -52,13 +72,16 @@ def _long_axis(shape: tuple[Any, ...]) -> int | None:
 
 
 class HostExecutor:
-    def __init__(self, program: CudaProgram, cq: Any = None, chunk: int = 262144):
+    def __init__(self, program: Any, cq: Any = None, chunk: int = 262144):
         import torch
 
         self.program = program
-        self.einsum = program.einsum
+        self.spec: HostSpec = (program.host_spec() if hasattr(program, "host_spec")
+                               else einsum_host_spec(program.einsum))
         self.cq: CudaQueue = as_queue(cq)
         self.chunk = int(chunk)
+        if self.chunk < 1:
+            raise ValueError("chunk must be positive")
         self.lib = _cabi.lib()
         dev = self.cq.torch_device
         self._streams = {k: torch.cuda.Stream(device=dev) for k in ("h2d", "run", "d2h")}
@@ -92,13 +115,15 @@ class HostExecutor:
     def __call__(self, outputs: dict[str, np.ndarray] | None = None, **arrays: np.ndarray) -> dict[str, np.ndarray]:
         import torch
 
-        es = self.einsum
+        spec = self.spec
         sizes: dict[str, int] = {}
-        for name, shape in es.arg_to_shape.items():
+        for name, shape in spec.in_shapes.items():
+            if name not in arrays:
+                raise TypeError(f"missing input array '{name}'")
             a = arrays[name]
             if not isinstance(a, np.ndarray) or not a.flags.c_contiguous:
                 raise TypeError(f"'{name}' must be a C-contiguous numpy array")
-            if a.dtype != np.dtype(es.arg_to_dtype[name]) or a.ndim != len(shape):
+            if a.dtype != spec.in_dtypes[name] or a.ndim != len(shape):
                 raise TypeError(f"'{name}' has wrong dtype or rank")
             for d, got in zip(shape, a.shape):
                 if isinstance(d, SizeParam):
@@ -106,33 +131,38 @@ class HostExecutor:
                         raise ValueError(f"inconsistent size parameter '{d.name}'")
                 elif int(d) != int(got):
                     raise ValueError(f"'{name}': expected {shape}, got {a.shape}")
+        unknown = set(arrays) - set(spec.in_shapes)
+        if unknown:
+            raise TypeError(f"unexpected arguments: {sorted(unknown)}")
         if len(sizes) > 1:
             raise NotImplementedError("one symbolic axis expected")
-        out_axis = _long_axis(es.shape)
         E = next(iter(sizes.values())) if sizes else 1
-        out_shape = tuple(E if isinstance(d, SizeParam) else int(d) for d in es.shape)
-        out_dtypes = [np.dtype(np.result_type(*[a.dtype for a in row])) for row in es.args]
-        outs = outputs or {}
-        for oname, odt in zip(es.output_names, out_dtypes):
+        out_axes = {n: _long_axis(s) for n, s in spec.out_shapes.items()}
+        out_shapes = {n: tuple(E if isinstance(d, SizeParam) else int(d) for d in s)
+                      for n, s in spec.out_shapes.items()}
+        outs = dict(outputs) if outputs else {}
+        for oname, odt in spec.out_dtypes.items():
             if oname not in outs:
-                outs[oname] = pinned_empty(out_shape, odt)
-            elif outs[oname].shape != out_shape or outs[oname].dtype != odt:
-                raise ValueError(f"output '{oname}' has wrong shape or dtype")
+                outs[oname] = pinned_empty(out_shapes[oname], odt)
+            elif outs[oname].shape != out_shapes[oname] or outs[oname].dtype != odt \
+                    or not outs[oname].flags.c_contiguous:
+                raise ValueError(f"output '{oname}' has wrong shape, dtype or layout")
+        chunked = bool(sizes) and all(ax is not None for ax in out_axes.values())
 
         s_h2d, s_run, s_d2h = (self._streams[k] for k in ("h2d", "run", "d2h"))
         self.h2d_bytes = self.d2h_bytes = 0
         with torch.cuda.device(self.cq.torch_device):
             # operands without the element axis: one copy, before everything else
-            for name, shape in es.arg_to_shape.items():
-                if _long_axis(shape) is None:
+            for name, shape in spec.in_shapes.items():
+                if _long_axis(shape) is None or not chunked:
                     a = arrays[name]
                     buf = self._dev_buf(("const", name), tuple(a.shape), a.dtype)
-                    self._copy(buf.data_ptr(), a.nbytes, a.ctypes.data, a.nbytes, a.nbytes, 1, 0, s_h2d)
+                    if a.nbytes:
+                        self._copy(buf.data_ptr(), a.nbytes, a.ctypes.data, a.nbytes, a.nbytes, 1, 0, s_h2d)
                     self.h2d_bytes += a.nbytes
                     self._const[name] = buf
-            if not sizes or out_axis is None:
-                # nothing to chunk over: single shot
-                chunks = [(0, E)]
+            if not chunked:
+                chunks = [(0, E)]          # nothing to chunk over: single shot
             else:
                 chunks = [(s, min(E, s + self.chunk)) for s in range(0, E, self.chunk)]
             ev_h2d = [None, None]
@@ -145,10 +175,10 @@ class HostExecutor:
                 if ev_run[slot] is not None:
                     s_h2d.wait_event(ev_run[slot])
                 dev_in: dict[str, Any] = {}
-                for name, shape in es.arg_to_shape.items():
+                for name, shape in spec.in_shapes.items():
                     ax = _long_axis(shape)
                     a = arrays[name]
-                    if ax is None:
+                    if ax is None or not chunked:
                         dev_in[name] = self._const[name]
                         continue
                     cshape = tuple(n if k == ax else int(a.shape[k]) for k in range(a.ndim))
@@ -166,26 +196,26 @@ class HostExecutor:
                 if ev_d2h[slot] is not None:
                     s_run.wait_event(ev_d2h[slot])
                 dev_out = {}
-                for oname, odt in zip(es.output_names, out_dtypes):
-                    cshape = tuple(
-                        n if (out_axis is not None and k == out_axis) else out_shape[k]
-                        for k in range(len(out_shape))
-                    )
+                for oname, odt in spec.out_dtypes.items():
+                    oshape, oax = out_shapes[oname], out_axes[oname]
+                    cshape = tuple(n if (chunked and k == oax) else oshape[k] for k in range(len(oshape)))
                     dev_out[oname] = self._dev_buf((slot, oname, n), cshape, odt)
                 self._exec(self._run_q, **dev_in, **dev_out)
                 ev_run[slot] = torch.cuda.Event()
                 ev_run[slot].record(s_run)
                 # ---- D2H
                 s_d2h.wait_event(ev_run[slot])
-                for oname in es.output_names:
-                    o, buf = outs[oname], dev_out[oname]
-                    if out_axis is None:
+                for oname in spec.out_dtypes:
+                    o, buf, oax = outs[oname], dev_out[oname], out_axes[oname]
+                    if not o.nbytes:
+                        continue
+                    if not chunked:
                         self._copy(o.ctypes.data, o.nbytes, buf.data_ptr(), o.nbytes, o.nbytes, 1, 1, s_d2h)
                         self.d2h_bytes += o.nbytes
                     else:
-                        inner = int(np.prod(o.shape[out_axis + 1:], dtype=np.int64)) * o.itemsize
-                        outer = int(np.prod(o.shape[:out_axis], dtype=np.int64))
-                        self._copy(o.ctypes.data + lo * inner, o.shape[out_axis] * inner,
+                        inner = int(np.prod(o.shape[oax + 1:], dtype=np.int64)) * o.itemsize
+                        outer = int(np.prod(o.shape[:oax], dtype=np.int64))
+                        self._copy(o.ctypes.data + lo * inner, o.shape[oax] * inner,
                                    buf.data_ptr(), n * inner, n * inner, outer, 1, s_d2h)
                         self.d2h_bytes += outer * n * inner
                 ev_d2h[slot] = torch.cuda.Event()

@@ -52,6 +52,24 @@ N_MIN_TIMING_ROUNDS = 10
 N_MIN_SIM_SECS = 2
 
 
+def fp32_validation_tol(program: Any) -> float:
+    """fp32 acceptance tolerance of :func:`validate_batched_einsum_transform`.
+
+    The reference's gate is ``atol = rtol = 1e-6`` against numpy's own fp32 evaluation
+    (reference ``measure.py:178-180``); it is kept for every kernel that accumulates in plain
+    fp32 (simt and generic variants, tensor-product).  The DG operator kernels' default fp32 path
+    is 3xTF32 on the tensor cores (``variant`` 0/1/3): split operands, fp32 accumulation with
+    truncation -- measured worst case 1.2e-6 against the fp64 oracle (div), plus numpy's own
+    ~4e-7.  For those variants only, the gate is :data:`FP32_VALIDATION_TOL` = 5e-6, half of the
+    1e-5 the drop-in contract allows for fp32.  (Behavioural difference vs the reference;
+    INTEGRATION.md section "fp32 validation gate".)"""
+    plan = getattr(program, "plan", None)
+    if plan is not None and plan.kernel_id in ("grad", "div", "lift_ef", "lift_fe", "opmat_se") \
+            and int(dict(getattr(program, "params", {})).get("variant", 0)) != 2:
+        return FP32_VALIDATION_TOL
+    return 1e-6
+
+
 def get_real_dtype(dtype: np.dtype[Any]) -> np.dtype[Any]:
     return np.empty(0, dtype=dtype).real.dtype
 
@@ -118,10 +136,7 @@ def generate_out_arrays(
     outs = {}
     for name, row in zip(einsum.output_names, einsum.args):
         dt = np.result_type(*[a.dtype for a in row])
-        tdt = {np.dtype("float64"): torch.float64, np.dtype("float32"): torch.float32}[
-            np.dtype(dt)
-        ]
-        outs[name] = torch.zeros(shape, dtype=tdt, device=q.torch_device)
+        outs[name] = torch.zeros(shape, dtype=getattr(torch, np.dtype(dt).name), device=q.torch_device)
     return Map(outs)
 
 
@@ -171,12 +186,7 @@ def validate_batched_einsum_transform(
             raise RuntimeError(f"dtype mismatch for output '{name}'")
         real = get_real_dtype(ref_out.dtype)
         if real == np.float32:
-            # reference: 1e-6 against numpy's own fp32 evaluation.  Two correct fp32 evaluations of
-            # these 105-term all-positive sums differ by ~1e-6 (summation order), and the tensor-core
-            # path accumulates with truncation (measured: 1.2e-6 worst for div, < 1e-6 for grad and
-            # lift), so the gate is FP32_VALIDATION_TOL = 5e-6 -- half of the 1e-5 the drop-in
-            # contract allows for fp32 -- instead of 1e-6.
-            atol = rtol = FP32_VALIDATION_TOL
+            atol = rtol = fp32_validation_tol(program)
         elif real == np.float64:
             atol = rtol = 1e-10
         else:

@@ -61,6 +61,40 @@ FLOPS_PER_ELEMENT = 7980 + 7980 + 17040
 BYTES_PER_ELEMENT = {np.dtype("float64"): 5384, np.dtype("float32"): 2692}
 
 
+class Wave3DProgram:
+    """The operator as a *program* (what ``generate_cuda`` returns for a single einsum): yields the
+    device executor, and describes its host boundary so that
+    :class:`feinsum_b200.host_exec.HostExecutor` can pipeline it over element chunks."""
+
+    kernel_id = "wave3d"
+
+    def __init__(self, dtype: Any = "float64", **params: int):
+        self.dtype = np.dtype(dtype)
+        self.params = dict(params)
+
+    def with_params(self, **params: int) -> "Wave3DProgram":
+        return Wave3DProgram(self.dtype, **{**self.params, **params})
+
+    def executor(self, cq: Any = None, **_unused: Any) -> "Wave3DExecutor":
+        return Wave3DExecutor(cq, self.dtype, **self.params)
+
+    def host_spec(self) -> Any:
+        from feinsum_b200.einsum import SizeParam
+        from feinsum_b200.host_exec import HostSpec
+
+        E = SizeParam("E")
+        ins, outs = shapes(0)
+        sym = lambda shp, pos: tuple(E if k == pos else d for k, d in enumerate(shp))  # noqa: E731
+        e_axis = {"J": 2, "v": 1, "u": 0, "Jface": 1, **{f"F_{k}": 1 for k in range(4)},
+                  "div_out": 0, "grad_out": 1, **{f"lift_{k}": 0 for k in range(4)}}
+        return HostSpec(
+            {n: (sym(s, e_axis[n]) if n in e_axis else s) for n, s in ins.items()},
+            {n: self.dtype for n in ins},
+            {n: sym(s, e_axis[n]) for n, s in outs.items()},
+            {n: self.dtype for n in outs},
+        )
+
+
 class Wave3DExecutor:
     """``evt, outs = Wave3DExecutor(cq)(cq, J=..., D=..., ...)`` -- torch CUDA tensors in,
     dict of the six outputs back (pre-allocated outputs may be passed by name)."""

@@ -21,9 +21,10 @@
  *     (a cudaStream_t passed as void*), like the reference's in-order queue.
  *   - return value: 0 on success, a positive cudaError_t, or a negative
  *     FNSM_E_* code.  fnsm_b200_strerror() decodes all three.
- *   - thread safety: entry points keep no mutable global state except a
- *     per-device attribute cache guarded by a mutex; concurrent calls on
- *     distinct streams are safe.
+ *   - thread safety: concurrent calls on distinct streams are safe.  Global
+ *     state: a per-device attribute cache guarded by a mutex, a relaxed atomic
+ *     launch counter (fnsm_b200_launch_count), per-thread caches of encoded TMA
+ *     descriptors, and the per-kernel "shared memory opted in" flags (atomics).
  *   - `cfg` may be NULL (built-in default launch configuration).  A config
  *     outside the legal space yields FNSM_E_BAD_CONFIG -- the tuner maps that
  *     to InvalidParameterError (reference tuning/__init__.py:557-559).
@@ -40,7 +41,11 @@ extern "C" {
 #define FNSM_ABI_VERSION 1
 
 /* dtype codes (reference: BatchedEinsum.arg_to_dtype, einsum.py:262-272) */
-enum { FNSM_F64 = 0, FNSM_F32 = 1 };
+enum {
+  FNSM_F64 = 0, FNSM_F32 = 1,
+  /* generic kernel only (reference measure.py:63-77 generates ints and complex too): */
+  FNSM_I32 = 2, FNSM_I64 = 3, FNSM_C64 = 4, FNSM_C128 = 5
+};
 
 /* error codes */
 enum {
@@ -105,7 +110,7 @@ typedef struct fnsm_einsum_desc {
   int32_t n_free;                         /* output rank; indices [0,n_free) are the output's, in order */
   int32_t n_sum;                          /* contracted indices [n_free, n_free+n_sum)                  */
   int32_t n_operands;
-  int32_t dtype;                          /* FNSM_F64 / FNSM_F32 (all operands and the output)          */
+  int32_t dtype;                          /* FNSM_F64 .. FNSM_C128 (all operands and the output)        */
   int64_t extent[FNSM_MAX_INDICES];       /* symbolic extents already bound                             */
   int64_t out_stride[FNSM_MAX_INDICES];   /* element strides of the output per free index               */
   int64_t in_stride[FNSM_MAX_OPERANDS][FNSM_MAX_INDICES]; /* 0 if the operand lacks the index; summed if it repeats */
@@ -134,8 +139,10 @@ int fnsm_b200_opmat_batch(int32_t kind, int32_t dtype,
                           int64_t E, const fnsm_cfg* cfg, void* stream);
 
 /* ------------------------------------------------------------------------
- * wave_3d_p4: div(v) + grad(u) + 4-field face-mass lift in ONE launch,
- * sharing J and the resident operator matrices.
+ * wave_3d_p4: div(v) + grad(u) + 4-field face-mass lift behind ONE call on one
+ * stream (three kernel launches, the 2nd and 3rd with programmatic dependent
+ * launch so that a kernel's tail overlaps the next prologue; the einsums share
+ * only J -- 72 of 5 456 B per element -- and the operator matrices).
  * replaces: the three autotuned kernels of examples/wave_3d_p4_auto.py:16-63.
  * ---------------------------------------------------------------------- */
 typedef struct fnsm_wave_args {

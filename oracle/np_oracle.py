@@ -103,9 +103,11 @@ def assert_matches(
 ) -> None:
     """reference ``measure.py:167-192`` with selectable tolerance set.
 
-    ``north_star=True``: rtol 1e-12 (fp64) / 1e-5 (fp32) and a matching atol
-    scaled by the magnitude of the reference output (inputs are in [0,1), the
-    outputs are sums of <= ~10^2 positive products)."""
+    ``north_star=True``: the drop-in contract's rtol 1e-12 (fp64) / 1e-5 (fp32),
+    element by element.  The only absolute slack is 1e-3 of that, scaled by the
+    largest reference magnitude -- it exists for exact zeros, not as headroom
+    (inputs are in [0,1): the outputs are sums of <= ~10^2 positive products, no
+    cancellation)."""
     if set(got) != set(ref):
         raise RuntimeError(f"Output names mismatch: {sorted(got)} vs {sorted(ref)}")
     for name in sorted(ref):
@@ -118,7 +120,7 @@ def assert_matches(
         if north_star:
             rtol = NORTH_STAR_RTOL[np.dtype(real)]
             scale = float(np.max(np.abs(r))) if r.size else 1.0
-            np.testing.assert_allclose(g, r, rtol=rtol, atol=rtol * scale, err_msg=name)
+            np.testing.assert_allclose(g, r, rtol=rtol, atol=1e-3 * rtol * scale, err_msg=name)
         else:
             tol = REFERENCE_TOL[np.dtype(real)]
             np.testing.assert_allclose(g, r, rtol=tol, atol=tol, err_msg=name)

@@ -74,3 +74,52 @@ def test_program_params_are_functional():
     p2 = prog.with_params(variant=2, tile_e=32)
     assert dict(prog.params) == {} and dict(p2.params) == {"variant": 2, "tile_e": 32}
     assert p2.kernel_id == "div" and np.dtype("float64") in set(E.div().arg_to_dtype.values())
+
+
+def test_shapes_the_opmat_kernels_cannot_hold_go_to_generic():
+    """extents without a tensor instantiation that the simt fallback rejects (n_outer > 4 for
+    grad/div; operator + element tile beyond the 227 KB of shared memory) must reach the generic kernel
+    instead of failing at launch -- the reference runs any BatchedEinsum."""
+    from feinsum_b200.codegen.cuda import opmat_kernel_available
+
+    assert classify(E.grad(ndim=5, ndof=6)).kernel_id == "generic"
+    assert classify(E.div(ndim=5, ndof=6)).kernel_id == "generic"
+    assert classify(E.grad(ndim=4, ndof=6)).kernel_id == "grad"
+    # p = 7 tets: D(3,120,120) fp64 = 345 KB
+    assert classify(E.grad(ndof=120)).kernel_id == "generic"
+    assert classify(E.div(ndof=120)).kernel_id == "generic"
+    assert classify(E.grad(ndof=120, dtype="float32")).kernel_id == "grad"      # 173 KB + tile fits
+    assert classify(E.lift_ef(nface=6, nvol=125, nfd=25)).kernel_id == "lift_ef"  # 150 KB + tile
+    assert classify(E.lift_ef(nface=6, nvol=216, nfd=36)).kernel_id == "generic"  # 373 KB
+    # every shape with a tensor-core kernel stays where it was
+    for nd, nfd in ((4, 3), (10, 6), (20, 10), (35, 15)):
+        assert classify(E.grad(ndof=nd)).kernel_id == "grad"
+        assert classify(E.lift_fe(nvol=nd, nfd=nfd)).kernel_id == "lift_fe"
+    assert opmat_kernel_available("div", np.dtype("float64"), 3, 56, 56)          # p = 5: simt, 75 KB
+    assert not opmat_kernel_available("div", np.dtype("float64"), 3, 120, 120)
+
+
+def test_loopy_only_entry_points_say_what_to_use_instead():
+    """reference src/feinsum/__init__.py:3-6,19-24: names resolve, calls raise NotImplementedError."""
+    import pytest
+
+    for name in ("generate_loopy", "generate_loopy_with_opt_einsum_schedule", "get_a_matched_einsum",
+                 "get_call_ids", "identify_as_einsum", "match_t_unit_to_einsum"):
+        fn = getattr(f, name)
+        with pytest.raises(NotImplementedError, match="B200 backend"):
+            fn(E.grad())
+    with pytest.raises(AttributeError):
+        f.no_such_name  # noqa: B018
+
+
+def test_wave3d_program_host_spec():
+    from feinsum_b200 import wave3d
+    from feinsum_b200.einsum import SizeParam
+
+    spec = wave3d.Wave3DProgram("float32").host_spec()
+    assert set(spec.in_shapes) == set(wave3d.INPUTS) and set(spec.out_shapes) == set(wave3d.OUTPUTS)
+    ins, outs = wave3d.shapes(7)
+    for n, s in {**spec.in_shapes, **spec.out_shapes}.items():
+        conc = tuple(7 if isinstance(d, SizeParam) else d for d in s)
+        assert conc == {**ins, **outs}[n]
+    assert spec.in_shapes["D"] == (3, 35, 35) and spec.in_dtypes["J"] == np.dtype("float32")

@@ -345,3 +345,35 @@ def test_launches_are_counted_and_native(cq):
     before = _cabi.launch_count()
     check(E.div(), 64, cq)
     assert _cabi.launch_count() > before
+
+
+def test_shapes_beyond_the_opmat_kernels_run_generic(cq):
+    # n_outer = 5 and a 345 KB operator used to fail at launch (UNSUPPORTED / BAD_CONFIG)
+    check(E.grad(ndim=5, ndof=6), 50, cq)
+    check(E.div(ndim=5, ndof=6), 50, cq)
+    check(E.div(ndof=120), 9, cq)
+
+
+@pytest.mark.parametrize("dtype", ["int32", "int64", "complex64", "complex128"])
+def test_generic_integer_and_complex_operands(cq, dtype):
+    """The IR accepts ints and complex (reference measure.py:63-77 generates them,
+    codegen/loopy.py:258-262 types the result); they run on the generic kernel."""
+    e = f.einsum("xre,rij,ej->xei", f.array("J", (2, 2, "E"), dtype), f.array("D", (2, 5, 5), dtype),
+                 f.array("u", ("E", 5), dtype))
+    ins = np_oracle.generate_input_arrays(e, 37, 2)
+    assert ins["u"].dtype == np.dtype(dtype)
+    got = run(e, ins, cq)
+    ref = np_oracle.reference_outputs(e, ins)
+    assert got["_fe_out"].dtype == np.dtype(dtype)
+    if np.dtype(dtype).kind == "i":
+        assert np.array_equal(got["_fe_out"], ref["_fe_out"])          # integer work: bit-exact
+    else:
+        np.testing.assert_allclose(got["_fe_out"], ref["_fe_out"],
+                                   rtol=1e-5 if dtype == "complex64" else 1e-12)
+
+
+def test_generic_rejects_mixed_row_dtypes(cq):
+    e = f.batched_einsum("ij,j->i", [[f.array("A", ("I", 4), "float64"), f.array("x", 4, "float64")],
+                                     [f.array("B", ("I", 4), "float32"), f.array("y", 4, "float32")]])
+    with pytest.raises(NotImplementedError):
+        generate_cuda(e).executor(cq)

@@ -1,0 +1,78 @@
+"""compute-sanitizer over small-E launches of every kernel family.
+
+``tools/sanitize_target`` (a C++ client of the C ABI, built by ``__graft_entry__.build()``) launches the
+DMMA kernels (TMA and plain-load producers), the generic DMMA / TF32 kernels, the tcgen05 + TMEM kernels, the
+mma.sync kernels, simt, tensor-product, generic and the wave operator.  ``FNSM_B200_MAX_SMS=6`` shrinks every
+persistent grid so each warp walks many work items: the mbarrier phase flips, slot re-arming and stage reuse
+that only show after the first item are all exercised.  Logs go to ``gpurun_out/sanitizer_<tool>.log``
+(copied to ``profiles/`` per round)."""
+
+import os
+import shutil
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TARGET = os.path.join(ROOT, "tools", "sanitize_target")
+
+
+def _sanitizer():
+    for cand in (shutil.which("compute-sanitizer"), "/usr/local/cuda/bin/compute-sanitizer"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def _run(tool, families, extra=()):
+    exe = _sanitizer()
+    if exe is None:
+        pytest.skip("compute-sanitizer not installed")
+    if not os.path.exists(TARGET):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    env = dict(os.environ, FNSM_B200_MAX_SMS="6")
+    cmd = [exe, "--tool", tool, "--error-exitcode", "99", *extra, TARGET, *families]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1500)
+    out = res.stdout + res.stderr
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"sanitizer_{tool}.log"), "a") as fh:
+        fh.write("$ " + " ".join(cmd) + "\n" + out + "\n")
+    return res.returncode, out
+
+
+ALL = ["dmma", "dmma_plain", "dmma_gen", "tc32", "tf32", "tf32_gen", "simt", "tp", "generic", "wave"]
+
+
+def test_target_runs_clean_without_sanitizer():
+    if not os.path.exists(TARGET):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    res = subprocess.run([TARGET, *ALL], capture_output=True, text=True,
+                         env=dict(os.environ, FNSM_B200_MAX_SMS="6"), timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "MISMATCH" not in res.stdout
+
+
+def test_memcheck():
+    rc, out = _run("memcheck", ALL)
+    assert rc == 0 and "ERROR SUMMARY: 0 errors" in out, out[-4000:]
+    assert "MISMATCH" not in out
+
+
+def test_synccheck():
+    rc, out = _run("synccheck", ALL)
+    assert rc == 0 and "ERROR SUMMARY: 0 errors" in out, out[-4000:]
+
+
+@pytest.mark.parametrize("families", [["dmma", "dmma_plain", "wave"], ["dmma_gen", "tf32", "tf32_gen", "simt", "tp"],
+                                      ["tc32"]])
+def test_racecheck(families):
+    """Shared-memory hazards.  The kernels hand shared memory between the generic proxy and the async proxy
+    (TMA) through mbarriers / bulk-group waits and between warps through __syncwarp / named barriers."""
+    rc, out = _run("racecheck", families, ("--racecheck-report", "all"))
+    assert rc == 0 and "RACECHECK SUMMARY: 0 hazards" in out, out[-4000:]
