@@ -649,12 +649,12 @@ def main() -> None:
             w = Work(name)
             n = n or w.default_e
             key = name + (f"@{n}" if n != w.default_e else "") + ("+l2flush" if flush else "")
-            suite[key] = bench.run_workload(w, n, args.suite_steps, 3, flush=flush)
+            suite[key] = bench.run_workload(w, n, args.suite_steps, 3, flush=flush, sample_clocks=True)
             bench.release()
         for name in STRONG_SUITE:
             w = Work(name)
             n = STRONG_TOTAL // world
-            ent = bench.run_workload(w, n, args.suite_steps, 3)
+            ent = bench.run_workload(w, n, args.suite_steps, 3, sample_clocks=True)
             ent["elements_total"] = n * world
             strong[name] = ent
             bench.release()

@@ -90,14 +90,15 @@ static int opmat_dispatch(int kind, int dtype, const void* jac, const void* op,
   int variant = cfg ? cfg->variant : 0;    // 0: library default
   if (variant < 0 || variant > 3) return FNSM_E_BAD_CONFIG;
   // variant 1 = mma.sync tensor path (fp64 DMMA, fp32 3xTF32; p = 4 tuned, p = 1..3 generic), 2 = simt (any shape),
-  // 3 = tcgen05 3xTF32 (fp32, tets p = 1..4, operands must qualify for TMA: E % 4 == 0, 16-byte aligned bases)
+  // 3 = tcgen05 3xTF32 (fp32, tets p = 1..4; TMA producer when E % 4 == 0 and the bases are 16-byte aligned,
+  //     cp.async producer + plain vector stores otherwise)
   const bool tensor_ok = dmma_supported(kind, n_outer, ni, nj);
   const bool tc_ok = dtype == FNSM_F32 && tc32_supported(kind, n_outer, ni, nj);   // tets p = 1..4
   const bool gen_ok = dmma_gen_supported(kind, n_outer, ni, nj);   // generic warp-per-chunk tensor kernels, tets p = 1..3
   if (variant == 1 && !tensor_ok && !gen_ok) return FNSM_E_UNSUPPORTED;
   if (variant == 3 && !tc_ok) return FNSM_E_UNSUPPORTED;
   const bool is_auto = variant == 0;
-  // auto: fp32 tets p = 1..4 -> tcgen05 (falls back to variant 1 when the operands do not qualify for TMA);
+  // auto: fp32 tets p = 1..4 -> tcgen05;
   // fp64 -> DMMA (tuned p = 4 kernels, generic p = 1..3 kernel); every other shape -> simt
   if (is_auto) variant = tc_ok ? 3 : ((tensor_ok || gen_ok) ? 1 : 2);
   for (int r0 = 0; r0 < b; r0 += 8) {
@@ -112,12 +113,9 @@ static int opmat_dispatch(int kind, int dtype, const void* jac, const void* op,
     if (variant == 1 && dtype == FNSM_F64)
       rc = tensor_ok ? launch_dmma(kind, jac, op, rows, nr, n_outer, ni, nj, E, cfg, di, st)
                      : launch_dmma_gen(kind, jac, op, rows, nr, ni, E, cfg, di, st);
-    else if (variant == 3) {
-      rc = launch_tc32(kind, jac, op, rows, nr, ni, E, di, st);
-      if (rc == FNSM_E_ALIGNMENT && is_auto)
-        rc = tensor_ok ? launch_tf32(kind, jac, op, rows, nr, E, cfg, di, st)
-                       : launch_tf32_gen(kind, jac, op, rows, nr, ni, E, cfg, di, st);
-    } else if (variant == 1)
+    else if (variant == 3)
+      rc = launch_tc32(kind, jac, op, rows, nr, ni, E, di, st, cfg && (cfg->reserved[0] & 1));
+    else if (variant == 1)
       rc = tensor_ok ? launch_tf32(kind, jac, op, rows, nr, E, cfg, di, st)
                      : launch_tf32_gen(kind, jac, op, rows, nr, ni, E, cfg, di, st);
     else if (dtype == FNSM_F64)

@@ -32,7 +32,8 @@
 //   * elements are permuted inside a chunk (el = 4*(g&3) + (g>>2) + 2m) so the
 //     stride-35 / stride-15 rows read by a half-warp fall into distinct banks.
 //
-// Unaligned inputs (odd E, misaligned base, tail chunk) take a plain-load path.
+// Unaligned inputs (odd E, misaligned base) take the plain producer: 8-byte cp.async by the lanes of the owning
+// warp, completing on the same mbarrier, results through coalesced stores from the stage.
 #pragma once
 #include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through cudart)
 #include <utility>
@@ -120,6 +121,17 @@ __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 lanes
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
   return v;
+}
+
+// 8-byte asynchronous global -> shared copy (always legal for fp64 operands) and its completion on an mbarrier:
+// the plain (non-TMA) producer of the DMMA kernels.  A warp's lanes issue the copies of its next work item and arrive
+// on the slot's barrier through their cp.async groups (barrier count 32 instead of 1), so the loads still land under
+// the DMMA stream exactly like the TMA loads do.  (Round 1 copied synchronously: LDG -> STS -> arrive.)
+__device__ __forceinline__ void cp_async8(double* dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
 // lets a kernel launched with programmatic stream serialization behind this one start as SMs free up (launch_k)
@@ -224,16 +236,18 @@ __device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps
       tma_load_2d(s + 3 * L::U_SLAB, &maps->jac, (int)e0, 0, bar);              // J[9][16 el]
     }
   } else {
+    // rows of elements past E are not copied: they hold stale (finite or not) data, are computed -- the rows of a
+    // DMMA tile are independent -- and never stored
     const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-    for (int x = 0; x < 3; ++x)
-      for (int k = lane; k < L::U_SLAB; k += 32)
-        s[x * L::U_SLAB + k] = (k < ne * 35) ? ug[((long long)x * E + e0) * 35 + k] : 0.0;
+    for (int x = 0; x < 3; ++x) {
+      const double* src = ug + ((long long)x * E + e0) * 35;
+      for (int k = lane; k < ne * 35; k += 32) cp_async8(s + x * L::U_SLAB + k, src + k);
+    }
     for (int k = lane; k < 9 * kCH; k += 32) {
       const int xr = k / kCH, el = k - xr * kCH;
-      s[3 * L::U_SLAB + k] = (el < ne) ? Jg[(long long)xr * E + e0 + el] : 0.0;
+      if (el < ne) cp_async8(s + 3 * L::U_SLAB + k, Jg + (long long)xr * E + e0 + el);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar);
+    cp_async_arrive_noinc(bar);
   }
 }
 
@@ -259,7 +273,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
-    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
+    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], (flags & kFlagTma) ? 1 : 32);   // plain producer: every lane arrives
     *work_ctr = 0u;
     mbar_fence_init();
   }
@@ -483,13 +497,12 @@ __device__ __forceinline__ void grad_issue(double* s, uint64_t* bar, const OpMap
     }
   } else {
     const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-    for (int k = lane; k < L::U_SLAB; k += 32) s[k] = (k < ne * 35) ? ug[e0 * 35 + k] : 0.0;
+    for (int k = lane; k < ne * 35; k += 32) cp_async8(s + k, ug + e0 * 35 + k);
     for (int k = lane; k < 9 * kCH; k += 32) {
       const int xr = k / kCH, el = k - xr * kCH;
-      s[L::U_SLAB + k] = (el < ne) ? Jg[(long long)xr * E + e0 + el] : 0.0;
+      if (el < ne) cp_async8(s + L::U_SLAB + k, Jg + (long long)xr * E + e0 + el);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar);
+    cp_async_arrive_noinc(bar);
   }
 }
 
@@ -552,7 +565,7 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
-    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
+    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], (flags & kFlagTma) ? 1 : 32);   // plain producer: every lane arrives
     *work_ctr = 0u;
     mbar_fence_init();
   }
@@ -651,17 +664,15 @@ __device__ __forceinline__ void lift_issue(double* s, uint64_t* bar, const CUten
     }
   } else {
     const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-    for (int f = 0; f < 4; ++f)
-      for (int k = lane; k < L::V_SLAB; k += 32)
-        s[f * L::V_SLAB + k] = (k < ne * 15) ? vg[((long long)f * E + e0) * 15 + k] : 0.0;
-    for (int k = lane; k < 4 * kCH; k += 32) {
-      double v = 0.0;
-      if (FE) { const int f = k / kCH, el = k - f * kCH; if (el < ne) v = Jg[(long long)f * E + e0 + el]; }
-      else    { const int el = k / 4; if (el < ne) v = Jg[e0 * 4 + k]; }
-      s[4 * L::V_SLAB + k] = v;
+    for (int f = 0; f < 4; ++f) {
+      const double* src = vg + ((long long)f * E + e0) * 15;
+      for (int k = lane; k < ne * 15; k += 32) cp_async8(s + f * L::V_SLAB + k, src + k);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar);
+    for (int k = lane; k < 4 * kCH; k += 32) {
+      if (FE) { const int f = k / kCH, el = k - f * kCH; if (el < ne) cp_async8(s + 4 * L::V_SLAB + k, Jg + (long long)f * E + e0 + el); }
+      else    { const int el = k / 4; if (el < ne) cp_async8(s + 4 * L::V_SLAB + k, Jg + e0 * 4 + k); }
+    }
+    cp_async_arrive_noinc(bar);
   }
 }
 
@@ -681,7 +692,7 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
-    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], 1);
+    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], (flags & kFlagTma) ? 1 : 32);   // plain producer: every lane arrives
     *work_ctr = 0u;
     mbar_fence_init();
   }

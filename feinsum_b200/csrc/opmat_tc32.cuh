@@ -99,6 +99,57 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 
+// ------------------------------------------- plain (non-TMA) producer / drain -----
+// Operands that do not qualify for tensor maps (E % 4 != 0: the rows of every array whose element axis is not
+// leading start at addresses that are not multiples of 16; or a base pointer that is not 16-byte aligned) used to fall
+// off the tcgen05 kernels onto the mma.sync ones (63-77 % of roofline instead of 94-99 %).  They now run the SAME
+// kernels with TMA = false: the threads of a group move a tile's rows with cp.async -- still asynchronous, still
+// completing on the slot's mbarrier (cp.async.mbarrier.arrive) -- and drain the stage with plain vector stores.
+// A slab lands at  slab_base + (global address & 15):  source and destination are congruent mod 16, so everything
+// but the ragged ends of a slab moves in 16-byte pieces; consumers read the slot with scalar 4-byte accesses
+// (rows of 35 / 15 floats), so the 0 / 4 / 8 / 12-byte shift costs them nothing.  TMA clipping / zero fill of the
+// tail tile becomes "copy only the valid rows" (stale rows are computed -- tile rows are independent -- and not stored).
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+// one arrival (counted in the barrier's expected count) once all earlier cp.async of this thread have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ int shift16(const void* p) { return (int)(reinterpret_cast<uintptr_t>(p) & 15); }
+// nbytes (multiple of 4) from the 4-byte aligned global address g to s_base + shift16(g); s_base is 16-byte aligned
+template <int NT>
+__device__ __forceinline__ void plain_load_async(unsigned char* s_base, const void* gp, int nbytes, int tid) {
+  const unsigned char* g = static_cast<const unsigned char*>(gp);
+  const int a = shift16(g);
+  const uint32_t s = smem_u32(s_base) + a;
+  int head = (16 - a) & 15;
+  if (head > nbytes) head = nbytes;
+  if (tid < (head >> 2)) cp_async4(s + 4 * tid, g + 4 * tid);
+  const int body = (nbytes - head) & ~15, end = head + body;
+  for (int o = head + 16 * tid; o < end; o += 16 * NT) cp_async16(s + o, g + o);
+  if (tid < ((nbytes - end) >> 2)) cp_async4(s + end + 4 * tid, g + end + 4 * tid);
+}
+// the reverse: nbytes staged at s_base + shift16(g) -> global g (streaming 16-byte stores + ragged ends)
+template <int NT>
+__device__ __forceinline__ void plain_store(void* gp, const unsigned char* s_base, int nbytes, int tid) {
+  unsigned char* g = static_cast<unsigned char*>(gp);
+  const int a = shift16(g);
+  const unsigned char* s = s_base + a;
+  int head = (16 - a) & 15;
+  if (head > nbytes) head = nbytes;
+  if (tid < (head >> 2)) *reinterpret_cast<float*>(g + 4 * tid) = *reinterpret_cast<const float*>(s + 4 * tid);
+  const int body = (nbytes - head) & ~15, end = head + body;
+  for (int o = head + 16 * tid; o < end; o += 16 * NT)
+    stg_stream(reinterpret_cast<float4*>(g + o), *reinterpret_cast<const float4*>(s + o));
+  if (tid < ((nbytes - end) >> 2))
+    *reinterpret_cast<float*>(g + end + 4 * tid) = *reinterpret_cast<const float*>(s + end + 4 * tid);
+}
+constexpr int kPlainPad = 128;      // slack per slab of a slot / stage in the non-TMA kernels (shift <= 12 B; keeps 128-B alignment)
+
 // ================================================================ GRAD =====
 
 constexpr int tc_pad(int v, int m) { return (v + m - 1) / m * m; }
@@ -128,22 +179,31 @@ struct GradTC {
   static constexpr int GROUP_BYTES = 2 * SLOT_BYTES + STAGE_BYTES;
   static constexpr int TMEM_COLS_PER_GROUP = 512 / GROUPS;      // 256 (240 used)
   static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 512;   // + mbarriers, TMEM base
+  // non-TMA variant: every slab of the slots and of the stage carries kPlainPad bytes of slack for its shift
+  static constexpr int OUT_SLAB_P = TM * ND * 4 + kPlainPad;
+  static constexpr int SLOT_P = SLOT_BYTES + kPlainPad;
+  static constexpr int STAGE_P = tc_pad(tc_max(3 * OUT_SLAB_P, 2 * A_BYTES), 128);
+  static constexpr int GROUP_P = 2 * SLOT_P + STAGE_P;
+  static constexpr size_t SMEM_P = B_BYTES + (size_t)GROUPS * GROUP_P + 512;
   static_assert(NB <= TMEM_COLS_PER_GROUP && NP + tc_pad(3 * ND, 8) <= TMEM_COLS_PER_GROUP, "TMEM budget");
-  static_assert(SMEM <= 227 * 1024, "shared-memory budget");
+  static_assert(SMEM_P <= 227 * 1024, "shared-memory budget");
   static_assert(SLOT_BYTES % 128 == 0, "TMA destination alignment");
 };
 
 struct GradTCMaps { CUtensorMap in, out; };
 
-template <int ND>
+// TMA = false: plain producer / drain (see "plain (non-TMA) producer" above); ug / outg are only used there
+template <int ND, bool TMA = true>
 __global__ void __launch_bounds__(GradTC<ND>::THREADS, 1)
 k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ Jg, const float* __restrict__ Dg,
-            long long E) {
+            const float* __restrict__ ug, float* __restrict__ outg, long long E) {
   using L = GradTC<ND>;
+  constexpr int GROUP_BYTES = TMA ? L::GROUP_BYTES : L::GROUP_P, SLOT_PITCH = TMA ? L::SLOT_BYTES : L::SLOT_P;
+  constexpr int OUT_SLAB = TMA ? L::TM * ND * 4 : L::OUT_SLAB_P;     // bytes between the x-slabs of the stage
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* sB = smem_raw;
   unsigned char* groups = smem_raw + L::B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(groups + (size_t)L::GROUPS * L::GROUP_BYTES);   // [group][full0, full1, mma]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(groups + (size_t)L::GROUPS * GROUP_BYTES);   // [group][full0, full1, mma]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * L::GROUPS);
 
   const int warp = uniform_warp_idx();
@@ -151,9 +211,11 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
   const int row = (wq & 3) * 32 + (threadIdx.x & 31);    // element row of the tile = TMEM lane
   const int half = L::NH == 1 ? 0 : wq >> 2;             // which share of the row's columns (constant 0 for WPG = 4)
   const bool leader = wq == 0 && (threadIdx.x & 31) == 0;
+  const int gtid = (int)threadIdx.x - gq * L::GT;        // thread index inside the group
 
   if (threadIdx.x == 0) {
-    for (int k = 0; k < 3 * L::GROUPS; ++k) mbar_init(&bars[k], 1);
+    // plain producer: every thread of the group arrives on a slot's barrier (through its cp.async group)
+    for (int k = 0; k < 3 * L::GROUPS; ++k) mbar_init(&bars[k], (!TMA && k % 3 != 2) ? L::GT : 1);
     mbar_fence_init();
   }
   __syncwarp();
@@ -177,10 +239,15 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
   const uint32_t tmem_base = *tmem_slot + (uint32_t)gq * L::TMEM_COLS_PER_GROUP;
   const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp & 3) * 32u << 16);
 
-  unsigned char* gbase = groups + (size_t)gq * L::GROUP_BYTES;
-  float* slot[2] = {reinterpret_cast<float*>(gbase), reinterpret_cast<float*>(gbase + L::SLOT_BYTES)};
-  unsigned char* stage_b = gbase + 2 * L::SLOT_BYTES;
-  float* stage = reinterpret_cast<float*>(stage_b);
+  unsigned char* gbase = groups + (size_t)gq * GROUP_BYTES;
+  unsigned char* slot_b[2] = {gbase, gbase + SLOT_PITCH};
+  const int ushift = TMA ? 0 : shift16(ug);              // tile rows start at multiples of 512 ND bytes: one shift for all tiles
+  const float* slot[2] = {reinterpret_cast<const float*>(slot_b[0] + ushift), reinterpret_cast<const float*>(slot_b[1] + ushift)};
+  unsigned char* stage_b = gbase + 2 * SLOT_PITCH;
+  float* stage_x[3];
+#pragma unroll
+  for (int x = 0; x < 3; ++x)
+    stage_x[x] = reinterpret_cast<float*>(stage_b + x * OUT_SLAB + (TMA ? 0 : shift16(outg + (long long)x * E * ND)));
   uint64_t* full = &bars[3 * gq];
   uint64_t* mma_done = &bars[3 * gq + 2];
   const int bar_id = 1 + gq;
@@ -189,16 +256,23 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
   const long long tile0 = (long long)blockIdx.x * L::GROUPS + gq, tstride = (long long)gridDim.x * L::GROUPS;
   constexpr uint32_t idesc_wide = umma_idesc_tf32(L::TM, L::NB), idesc_half = umma_idesc_tf32(L::TM, L::N);
 
-  if (leader) {
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      const long long tl = tile0 + p * tstride;
-      if (tl < ntiles) {
+  // fetch tile tl into slot p.  TMA: the leader; plain: every thread of the group moves its share
+  auto fetch = [&](long long tl, int p) {
+    if constexpr (TMA) {
+      if (leader) {
         mbar_arrive_expect_tx(&full[p], L::SLOT_BYTES);
-        tma_load_2d(slot[p], &maps.in, 0, (int)(tl * (L::TM / 4)), &full[p]);
+        tma_load_2d(slot_b[p], &maps.in, 0, (int)(tl * (L::TM / 4)), &full[p]);
       }
+    } else {
+      const long long e0 = tl * L::TM;
+      const int rows = (int)(E - e0 < L::TM ? E - e0 : L::TM);
+      plain_load_async<L::GT>(slot_b[p], ug + e0 * ND, rows * ND * 4, gtid);
+      cp_async_arrive(&full[p]);
     }
-  }
+  };
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+    if (tile0 + p * tstride < ntiles) fetch(tile0 + p * tstride, p);
   // Jacobian of this thread's element, fetched one tile ahead (coalesced: J[xr][e])
   float Jn[9];
   {
@@ -220,7 +294,8 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
     }
     mbar_wait(&full[s], (it >> 1) & 1u);
     // the A operand aliases the output stage: the previous tile's bulk store must have read it out
-    if (leader) tma_store_wait_read();
+    // (plain drain: every thread finished its share of the copy before it got here)
+    if (TMA && leader) tma_store_wait_read();
     group_barrier(bar_id, L::GT);
     // ---- element row -> A_hi / A_lo (K-major canonical layout: 16-byte k-quads, rows 16 B apart) ----
     {
@@ -254,13 +329,9 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
         umma_tf32(tmem_base + L::NP, dal, db, idesc_half, true);      // corr += A_lo B_hi
       }
       umma_commit(mma_done);
-      // the slot has been consumed by every thread of the group: fetch the tile two steps ahead
-      const long long tl = tile + 2 * tstride;
-      if (tl < ntiles) {
-        mbar_arrive_expect_tx(&full[s], L::SLOT_BYTES);
-        tma_load_2d(slot[s], &maps.in, 0, (int)(tl * (L::TM / 4)), &full[s]);
-      }
     }
+    // the slot has been consumed by every thread of the group: fetch the tile two steps ahead
+    if (tile + 2 * tstride < ntiles) fetch(tile + 2 * tstride, s);
     mbar_wait(mma_done, it & 1u);
     tc_fence_after();
     // ---- TMEM -> registers (8 dofs = 24 columns at a time), J applied, staged as out[x][e][i] ----
@@ -282,19 +353,27 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
           const float T0 = m[3 * d] + c[3 * d], T1 = m[3 * d + 1] + c[3 * d + 1], T2 = m[3 * d + 2] + c[3 * d + 2];
 #pragma unroll
           for (int x = 0; x < 3; ++x)
-            stage[(x * L::TM + row) * ND + i] = fmaf(Jr[3 * x + 2], T2, fmaf(Jr[3 * x + 1], T1, Jr[3 * x] * T0));
+            stage_x[x][row * ND + i] = fmaf(Jr[3 * x + 2], T2, fmaf(Jr[3 * x + 1], T1, Jr[3 * x] * T0));
         }
       }
     }
     tc_fence_before();                                   // TMEM reads done before the next tile's MMAs
     fence_proxy_async();
     group_barrier(bar_id, L::GT);
-    if (leader) {
-      tma_store_3d(&maps.out, stage, 0, (int)(tile * (L::TM / 4)), 0);
-      tma_store_commit();
+    if constexpr (TMA) {
+      if (leader) {
+        tma_store_3d(&maps.out, stage_b, 0, (int)(tile * (L::TM / 4)), 0);
+        tma_store_commit();
+      }
+    } else {
+      const long long e0 = tile * L::TM;
+      const int rows = (int)(E - e0 < L::TM ? E - e0 : L::TM);
+#pragma unroll
+      for (int x = 0; x < 3; ++x)
+        plain_store<L::GT>(outg + ((long long)x * E + e0) * ND, stage_b + x * OUT_SLAB, rows * ND * 4, gtid);
     }
   }
-  if (leader) tma_store_wait_all();
+  if (TMA && leader) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(*tmem_slot, 512);
@@ -326,19 +405,27 @@ struct LiftTC {
   static_assert(A_LO_COL + K <= TMEM_COLS_PER_GROUP && K % 8 == 0, "TMEM budget");
   static_assert(SLOT_BYTES % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA alignment");
   static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 512;   // + mbarriers, TMEM base
+  // non-TMA variant (see GradTC): face slabs and the stage carry kPlainPad bytes of slack
+  static constexpr int V_SLAB_P = V_SLAB * 4 + kPlainPad;                       // bytes per face slab
+  static constexpr int SLOT_P = 4 * V_SLAB_P, STAGE_P = STAGE_BYTES + kPlainPad;
+  static constexpr int GROUP_P = 2 * SLOT_P + STAGE_P;
+  static constexpr size_t SMEM_P = B_BYTES + (size_t)GROUPS * GROUP_P + 512;
+  static_assert(SMEM_P <= 227 * 1024, "shared-memory budget");
 };
 
 struct LiftTCMaps { CUtensorMap in[8]; CUtensorMap out[8]; };
 
-template <int ND, int NFD, bool FE>
+template <int ND, int NFD, bool FE, bool TMA = true>
 __global__ void __launch_bounds__(LiftTC<ND, NFD>::THREADS, 1)
 k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ Jg, const float* __restrict__ Og,
-            int nrows, long long E) {
+            const __grid_constant__ OpmatRows rows, int nrows, long long E) {
   using L = LiftTC<ND, NFD>;
+  constexpr int GROUP_BYTES = TMA ? L::GROUP_BYTES : L::GROUP_P, SLOT_PITCH = TMA ? L::SLOT_BYTES : L::SLOT_P;
+  constexpr int V_SLAB_B = TMA ? L::V_SLAB * 4 : L::V_SLAB_P;       // bytes between the face slabs of a slot
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* sB = smem_raw;
   unsigned char* groups = smem_raw + L::B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(groups + (size_t)L::GROUPS * L::GROUP_BYTES);   // [group][full0, full1, mma]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(groups + (size_t)L::GROUPS * GROUP_BYTES);   // [group][full0, full1, mma]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * L::GROUPS);
 
   const int warp = uniform_warp_idx();
@@ -346,9 +433,10 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
   const int row = (wq & 3) * 32 + (threadIdx.x & 31);
   const int half = L::NH == 1 ? 0 : wq >> 2;
   const bool leader = wq == 0 && (threadIdx.x & 31) == 0;
+  const int gtid = (int)threadIdx.x - gq * L::GT;
 
   if (threadIdx.x == 0) {
-    for (int k = 0; k < 3 * L::GROUPS; ++k) mbar_init(&bars[k], 1);
+    for (int k = 0; k < 3 * L::GROUPS; ++k) mbar_init(&bars[k], (!TMA && k % 3 != 2) ? L::GT : 1);
     mbar_fence_init();
   }
   __syncwarp();
@@ -373,9 +461,9 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
   const uint32_t tmem_base = *tmem_slot + (uint32_t)gq * L::TMEM_COLS_PER_GROUP;
   const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp & 3) * 32u << 16);
 
-  unsigned char* gbase = groups + (size_t)gq * L::GROUP_BYTES;
-  float* slot[2] = {reinterpret_cast<float*>(gbase), reinterpret_cast<float*>(gbase + L::SLOT_BYTES)};
-  float* stage = reinterpret_cast<float*>(gbase + 2 * L::SLOT_BYTES);
+  unsigned char* gbase = groups + (size_t)gq * GROUP_BYTES;
+  unsigned char* slot_b[2] = {gbase, gbase + SLOT_PITCH};
+  unsigned char* stage_b = gbase + 2 * SLOT_PITCH;
   uint64_t* full = &bars[3 * gq];
   uint64_t* mma_done = &bars[3 * gq + 2];
   const int bar_id = 1 + gq;
@@ -387,25 +475,40 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
   const long long my_tiles = tile0 < ntiles ? (ntiles - tile0 + tstride - 1) / tstride : 0;
   const long long nitems = my_tiles * nrows;
 
-  auto issue = [&](long long item, int s) {             // leader only
+  // TMA: the leader; plain: every thread of the group moves its share of the four face slabs
+  auto issue = [&](long long item, int s) {
     const long long tl = tile0 + (item / nrows) * tstride;
     const int fld = (int)(item % nrows);
-    mbar_arrive_expect_tx(&full[s], L::SLOT_BYTES);
-    tma_load_3d(slot[s], &maps.in[fld], 0, (int)(tl * (L::TM / 4)), 0, &full[s]);
+    if constexpr (TMA) {
+      if (leader) {
+        mbar_arrive_expect_tx(&full[s], L::SLOT_BYTES);
+        tma_load_3d(slot_b[s], &maps.in[fld], 0, (int)(tl * (L::TM / 4)), 0, &full[s]);
+      }
+    } else {
+      const long long e0 = tl * L::TM;
+      const int nr = (int)(E - e0 < L::TM ? E - e0 : L::TM);
+      const float* vg = static_cast<const float*>(rows.field[fld]);
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        plain_load_async<L::GT>(slot_b[s] + f * V_SLAB_B, vg + ((long long)f * E + e0) * NFD, nr * NFD * 4, gtid);
+      cp_async_arrive(&full[s]);
+    }
   };
-  if (leader) {
-    if (nitems > 0) issue(0, 0);
-    if (nitems > 1) issue(1, 1);
-  }
+  if (nitems > 0) issue(0, 0);
+  if (nitems > 1) issue(1, 1);
+  const bool j_vec = TMA || shift16(Jg) == 0;            // J(E,4) rows are 16 bytes: vector load iff the base is aligned
   auto load_j = [&](long long tl, float (&J)[4]) {
     const long long e = tl * L::TM + row;
     if (tl < ntiles && e < E) {
       if (FE) {
 #pragma unroll
         for (int f = 0; f < 4; ++f) J[f] = __ldg(Jg + (long long)f * E + e);
-      } else {
+      } else if (j_vec) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(Jg) + e);
         J[0] = v.x; J[1] = v.y; J[2] = v.z; J[3] = v.w;
+      } else {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) J[f] = __ldg(Jg + e * 4 + f);
       }
     } else {
 #pragma unroll
@@ -427,7 +530,12 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
     mbar_wait(&full[s], (uint32_t)(it >> 1) & 1u);
     // ---- row of the slot -> A_hi / A_lo in TMEM ----
     {
-      const float* sv = slot[s] + row * NFD;
+      const float* svf[4];                     // this row in the four face slabs (plain: each slab has its own shift)
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const int sh = TMA ? 0 : shift16(static_cast<const float*>(rows.field[fld]) + (long long)f * E * NFD);
+        svf[f] = reinterpret_cast<const float*>(slot_b[s] + f * V_SLAB_B + sh) + row * NFD;
+      }
 #pragma unroll
       for (int c = 0; c < L::K / 8; ++c) {     // 8 k at a time
         if (L::NH > 1 && (c % L::NH) != half) continue;   // warp-uniform; c stays a compile-time constant
@@ -435,7 +543,7 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int k = 8 * c + q, f = k / NFD, j = k - NFD * f;
-          const float a = k < 4 * NFD ? Jf[f < 4 ? f : 3] * sv[(f < 4 ? f : 3) * L::V_SLAB + j] : 0.f;
+          const float a = k < 4 * NFD ? Jf[f < 4 ? f : 3] * svf[f < 4 ? f : 3][j] : 0.f;
           split_tf32(a, hi[q], lo[q]);
         }
         tmem_st8(tmem_lane + L::A_HI_COL + 8 * c, hi);
@@ -455,12 +563,15 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
         umma_tf32_ts(tmem_base + L::NP, tmem_base + L::A_LO_COL + 8 * ks, db, idesc_half, true);
       }
       umma_commit(mma_done);
-      if (it + 2 < nitems) { fence_proxy_async(); issue(it + 2, s); }
-      tma_store_wait_read();                             // the stage is free again (previous item's store)
+      if (TMA && it + 2 < nitems) fence_proxy_async();
     }
+    if (it + 2 < nitems) issue(it + 2, s);
+    if (TMA && leader) tma_store_wait_read();            // the stage is free again (previous item's store)
     mbar_wait(mma_done, (uint32_t)it & 1u);
     tc_fence_after();
-    group_barrier(bar_id, L::GT);                          // ... and every thread knows it
+    group_barrier(bar_id, L::GT);                          // ... and every thread knows it (plain: all drained it)
+    float* outp = static_cast<float*>(rows.out[fld]) + tile * L::TM * ND;
+    float* stage = reinterpret_cast<float*>(stage_b + (TMA ? 0 : shift16(outp)));
 #pragma unroll
     for (int q = 0; q < L::NQ; ++q) {
       if (L::NH > 1 && (q % L::NH) != half) continue;   // warp-uniform; q stays a compile-time constant
@@ -475,13 +586,18 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
     tc_fence_before();
     fence_proxy_async();
     group_barrier(bar_id, L::GT);
-    if (leader) {
-      tma_store_2d(&maps.out[fld], stage, 0, (int)(tile * (L::TM / 4)));
-      tma_store_commit();
+    if constexpr (TMA) {
+      if (leader) {
+        tma_store_2d(&maps.out[fld], stage_b, 0, (int)(tile * (L::TM / 4)));
+        tma_store_commit();
+      }
+    } else {
+      const long long e0 = tile * L::TM;
+      plain_store<L::GT>(outp, stage_b, (int)(E - e0 < L::TM ? E - e0 : L::TM) * ND * 4, gtid);
     }
     if (++fld == nrows) { fld = 0; tile += tstride; }
   }
-  if (leader) tma_store_wait_all();
+  if (TMA && leader) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(*tmem_slot, 512);
@@ -512,19 +628,27 @@ struct DivTC {
   static_assert(A_COL + 2 * A_BUF <= TMEM_COLS_PER_GROUP, "TMEM budget");
   static_assert(SLOT_BYTES % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA alignment");
   static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 512;   // + mbarriers, TMEM base
+  // non-TMA variant (see GradTC): the three x-slabs and the stage carry kPlainPad bytes of slack
+  static constexpr int U_SLAB_P = U_SLAB * 4 + kPlainPad;
+  static constexpr int SLOT_P = 3 * U_SLAB_P, STAGE_P = STAGE_BYTES + kPlainPad;
+  static constexpr int GROUP_P = SLOT_P + STAGE_P;
+  static constexpr size_t SMEM_P = B_BYTES + (size_t)GROUPS * GROUP_P + 512;
+  static_assert(SMEM_P <= 227 * 1024, "shared-memory budget");
 };
 
 struct DivTCMaps { CUtensorMap in, out; };
 
-template <int ND>
+template <int ND, bool TMA = true>
 __global__ void __launch_bounds__(DivTC<ND>::THREADS, 1)
 k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg, const float* __restrict__ Dg,
-           long long E) {
+           const float* __restrict__ ug, float* __restrict__ outg, long long E) {
   using L = DivTC<ND>;
+  constexpr int GROUP_BYTES = TMA ? L::GROUP_BYTES : L::GROUP_P, SLOT_PITCH = TMA ? L::SLOT_BYTES : L::SLOT_P;
+  constexpr int U_SLAB_B = TMA ? L::U_SLAB * 4 : L::U_SLAB_P;       // bytes between the x-slabs of the slot
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* sB = smem_raw;
   unsigned char* groups = smem_raw + L::B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(groups + (size_t)L::GROUPS * L::GROUP_BYTES);   // [group][full, mma0, mma1, mma2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(groups + (size_t)L::GROUPS * GROUP_BYTES);   // [group][full, mma0, mma1, mma2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * L::GROUPS);
 
   const int warp = uniform_warp_idx();
@@ -532,9 +656,10 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
   const int row = (wq & 3) * 32 + (threadIdx.x & 31);
   const int half = L::NH == 1 ? 0 : wq >> 2;
   const bool leader = wq == 0 && (threadIdx.x & 31) == 0;
+  const int gtid = (int)threadIdx.x - gq * L::GT;
 
   if (threadIdx.x == 0) {
-    for (int k = 0; k < 4 * L::GROUPS; ++k) mbar_init(&bars[k], 1);
+    for (int k = 0; k < 4 * L::GROUPS; ++k) mbar_init(&bars[k], (!TMA && k % 4 == 0) ? L::GT : 1);
     mbar_fence_init();
   }
   __syncwarp();
@@ -558,9 +683,14 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
   const uint32_t tmem_base = *tmem_slot + (uint32_t)gq * L::TMEM_COLS_PER_GROUP;
   const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp & 3) * 32u << 16);
 
-  unsigned char* gbase = groups + (size_t)gq * L::GROUP_BYTES;
-  float* slot = reinterpret_cast<float*>(gbase);
-  float* stage = reinterpret_cast<float*>(gbase + L::SLOT_BYTES);
+  unsigned char* gbase = groups + (size_t)gq * GROUP_BYTES;
+  unsigned char* slot_b = gbase;
+  unsigned char* stage_b = gbase + SLOT_PITCH;
+  float* stage = reinterpret_cast<float*>(stage_b + (TMA ? 0 : shift16(outg)));   // tiles start at multiples of 512 ND bytes
+  const float* sux[3];                                   // this thread's row in the three x-slabs
+#pragma unroll
+  for (int x = 0; x < 3; ++x)
+    sux[x] = reinterpret_cast<const float*>(slot_b + x * U_SLAB_B + (TMA ? 0 : shift16(ug + (long long)x * E * ND))) + row * ND;
   uint64_t* full = &bars[4 * gq];
   uint64_t* mma_done = &bars[4 * gq + 1];                // one per chunk
   const int bar_id = 1 + gq;
@@ -569,10 +699,23 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
   const long long tile0 = (long long)blockIdx.x * L::GROUPS + gq, tstride = (long long)gridDim.x * L::GROUPS;
   constexpr uint32_t idesc_wide = umma_idesc_tf32(L::TM, L::NB), idesc_half = umma_idesc_tf32(L::TM, L::N);
 
-  if (leader && tile0 < ntiles) {
-    mbar_arrive_expect_tx(full, L::SLOT_BYTES);
-    tma_load_3d(slot, &maps.in, 0, (int)(tile0 * (L::TM / 4)), 0, full);
-  }
+  // TMA: the leader; plain: every thread of the group moves its share of the three x-slabs
+  auto fetch = [&](long long tl) {
+    if constexpr (TMA) {
+      if (leader) {
+        mbar_arrive_expect_tx(full, L::SLOT_BYTES);
+        tma_load_3d(slot_b, &maps.in, 0, (int)(tl * (L::TM / 4)), 0, full);
+      }
+    } else {
+      const long long e0 = tl * L::TM;
+      const int nr = (int)(E - e0 < L::TM ? E - e0 : L::TM);
+#pragma unroll
+      for (int x = 0; x < 3; ++x)
+        plain_load_async<L::GT>(slot_b + x * U_SLAB_B, ug + ((long long)x * E + e0) * ND, nr * ND * 4, gtid);
+      cp_async_arrive(full);
+    }
+  };
+  if (tile0 < ntiles) fetch(tile0);
   float Jn[9];
   {
     const long long e = tile0 * L::TM + row;
@@ -591,7 +734,6 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
       for (int xr = 0; xr < 9; ++xr) Jn[xr] = (tn < ntiles && e < E) ? __ldg(Jg + (long long)xr * E + e) : 0.f;
     }
     mbar_wait(full, it & 1u);
-    const float* su = slot + row * ND;
 #pragma unroll
     for (int r = 0; r < L::NCHUNK; ++r) {
       const int buf = r & 1;
@@ -607,7 +749,7 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
           const int j = 8 * c + q;
           float w = 0.f;
           if (j < ND)
-            w = fmaf(Jr[6 + r], su[2 * L::U_SLAB + j], fmaf(Jr[3 + r], su[L::U_SLAB + j], Jr[r] * su[j]));
+            w = fmaf(Jr[6 + r], sux[2][j], fmaf(Jr[3 + r], sux[1][j], Jr[r] * sux[0][j]));
           split_tf32(w, hi[q], lo[q]);
         }
         tmem_st8(a_hi + 8 * c, hi);
@@ -627,16 +769,12 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
           umma_tf32_ts(tmem_base + L::N, ta + L::A_LO + 8 * ks, db, idesc_half, true);
         }
         umma_commit(&mma_done[r]);
-        if (r == L::NCHUNK - 1) {
-          // every thread is past its last read of the slot: fetch this group's next tile
-          const long long tl = tile + tstride;
-          if (tl < ntiles) {
-            fence_proxy_async();
-            mbar_arrive_expect_tx(full, L::SLOT_BYTES);
-            tma_load_3d(slot, &maps.in, 0, (int)(tl * (L::TM / 4)), 0, full);
-          }
-          tma_store_wait_read();                         // the stage is free again (previous tile's store)
-        }
+        if (TMA && r == L::NCHUNK - 1 && tile + tstride < ntiles) fence_proxy_async();
+      }
+      if (r == L::NCHUNK - 1) {
+        // every thread is past its last read of the slot: fetch this group's next tile
+        if (tile + tstride < ntiles) fetch(tile + tstride);
+        if (TMA && leader) tma_store_wait_read();        // the stage is free again (previous tile's store)
       }
     }
     mbar_wait(&mma_done[1], it & 1u);
@@ -657,12 +795,17 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
     tc_fence_before();
     fence_proxy_async();
     group_barrier(bar_id, L::GT);
-    if (leader) {
-      tma_store_2d(&maps.out, stage, 0, (int)(tile * (L::TM / 4)));
-      tma_store_commit();
+    if constexpr (TMA) {
+      if (leader) {
+        tma_store_2d(&maps.out, stage_b, 0, (int)(tile * (L::TM / 4)));
+        tma_store_commit();
+      }
+    } else {
+      const long long e0 = tile * L::TM;
+      plain_store<L::GT>(outg + e0 * ND, stage_b, (int)(E - e0 < L::TM ? E - e0 : L::TM) * ND * 4, gtid);
     }
   }
-  if (leader) tma_store_wait_all();
+  if (TMA && leader) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(*tmem_slot, 512);
@@ -689,92 +832,106 @@ inline bool tc32_supported(int kind, int n_outer, int ni, int nj) {
   return n_outer == 4 && ((ni == 4 && nj == 3) || (ni == 10 && nj == 6) || (ni == 20 && nj == 10) || (ni == 35 && nj == 15));
 }
 
-// returns FNSM_E_ALIGNMENT when the operands do not qualify (caller falls back to another variant)
+// Operands that qualify for tensor maps (E % 4 == 0, 16-byte aligned bases) take the TMA instantiation, everything
+// else the plain-producer instantiation of the same kernel.
 template <int ND>
 static int launch_grad_tc32(const float* J, const float* D, const float* u, float* out, long long E,
-                            const DevInfo& di, cudaStream_t st) {
+                            const DevInfo& di, cudaStream_t st, bool force_plain) {
   using L = GradTC<ND>;
-  if (E % 4 != 0 || E >= (1LL << 31) - L::TM || !aligned16(u) || !aligned16(out)) return FNSM_E_ALIGNMENT;
-  if (L::SMEM > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
-  GradTCMaps maps;
-  if (!map32_rows_box(&maps.in, u, E, ND, L::TM / 4) || !map32_slabs_box(&maps.out, out, E, ND, 3, L::TM / 4))
-    return FNSM_E_ALIGNMENT;
+  if (E >= (1LL << 31) - L::TM) return FNSM_E_UNSUPPORTED;
+  if (L::SMEM_P > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
   const long long ntiles = (E + L::TM - 1) / L::TM;
   const long long need = (ntiles + L::GROUPS - 1) / L::GROUPS;
   const unsigned grid = (unsigned)(di.sms < need ? di.sms : need);
-  if (int rc = set_smem(k_grad_tc32<ND>, L::SMEM)) return rc;
-  k_grad_tc32<ND><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, D, E);
+  GradTCMaps maps{};
+  const bool tma = !force_plain && E % 4 == 0 && aligned16(u) && aligned16(out) &&
+                   map32_rows_box(&maps.in, u, E, ND, L::TM / 4) && map32_slabs_box(&maps.out, out, E, ND, 3, L::TM / 4);
+  if (tma) {
+    if (int rc = set_smem(k_grad_tc32<ND, true>, L::SMEM)) return rc;
+    k_grad_tc32<ND, true><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, D, u, out, E);
+  } else {
+    if (int rc = set_smem(k_grad_tc32<ND, false>, L::SMEM_P)) return rc;
+    k_grad_tc32<ND, false><<<grid, L::THREADS, L::SMEM_P, st>>>(maps, J, D, u, out, E);
+  }
   return post_launch();
 }
 
 template <int ND, int NFD>
 static int launch_lift_tc32(int kind, const float* J, const float* O, const OpmatRows& rows, int nrows, long long E,
-                            const DevInfo& di, cudaStream_t st) {
+                            const DevInfo& di, cudaStream_t st, bool force_plain) {
   using L = LiftTC<ND, NFD>;
   const bool fe = kind == FNSM_OP_LIFT_FE;
-  if (E % 4 != 0 || E >= (1LL << 31) - L::TM || (!fe && !aligned16(J))) return FNSM_E_ALIGNMENT;
-  if (L::SMEM > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
-  LiftTCMaps maps;
-  for (int r = 0; r < nrows; ++r) {
-    if (!aligned16(rows.field[r]) || !aligned16(rows.out[r])) return FNSM_E_ALIGNMENT;
-    if (!map32_slabs_box(&maps.in[r], rows.field[r], E, NFD, 4, L::TM / 4) ||
-        !map32_rows_box(&maps.out[r], rows.out[r], E, ND, L::TM / 4))
-      return FNSM_E_ALIGNMENT;
-  }
+  if (E >= (1LL << 31) - L::TM) return FNSM_E_UNSUPPORTED;
+  if (L::SMEM_P > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
+  LiftTCMaps maps{};
+  bool tma = !force_plain && E % 4 == 0 && (fe || aligned16(J));
+  for (int r = 0; r < nrows && tma; ++r)
+    tma = aligned16(rows.field[r]) && aligned16(rows.out[r]) &&
+          map32_slabs_box(&maps.in[r], rows.field[r], E, NFD, 4, L::TM / 4) &&
+          map32_rows_box(&maps.out[r], rows.out[r], E, ND, L::TM / 4);
   const long long ntiles = (E + L::TM - 1) / L::TM;
   const long long need = (ntiles + L::GROUPS - 1) / L::GROUPS;
   const unsigned grid = (unsigned)(di.sms < need ? di.sms : need);
-  if (fe) {
-    if (int rc = set_smem(k_lift_tc32<ND, NFD, true>, L::SMEM)) return rc;
-    k_lift_tc32<ND, NFD, true><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, O, nrows, E);
-  } else {
-    if (int rc = set_smem(k_lift_tc32<ND, NFD, false>, L::SMEM)) return rc;
-    k_lift_tc32<ND, NFD, false><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, O, nrows, E);
-  }
+#define FNSM_LIFT_TC(FE_, TMA_, SMEM_)                                                          \
+  do {                                                                                          \
+    if (int rc = set_smem(k_lift_tc32<ND, NFD, FE_, TMA_>, SMEM_)) return rc;                   \
+    k_lift_tc32<ND, NFD, FE_, TMA_><<<grid, L::THREADS, SMEM_, st>>>(maps, J, O, rows, nrows, E); \
+  } while (0)
+  if (fe) { if (tma) FNSM_LIFT_TC(true, true, L::SMEM); else FNSM_LIFT_TC(true, false, L::SMEM_P); }
+  else    { if (tma) FNSM_LIFT_TC(false, true, L::SMEM); else FNSM_LIFT_TC(false, false, L::SMEM_P); }
+#undef FNSM_LIFT_TC
   return post_launch();
 }
 
 template <int ND>
 static int launch_div_tc32(const float* J, const float* D, const float* u, float* out, long long E,
-                           const DevInfo& di, cudaStream_t st) {
+                           const DevInfo& di, cudaStream_t st, bool force_plain) {
   using L = DivTC<ND>;
-  if (E % 4 != 0 || E >= (1LL << 31) - L::TM || !aligned16(u) || !aligned16(out)) return FNSM_E_ALIGNMENT;
-  if (L::SMEM > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
-  DivTCMaps maps;
-  if (!map32_slabs_box(&maps.in, u, E, ND, 3, L::TM / 4) || !map32_rows_box(&maps.out, out, E, ND, L::TM / 4))
-    return FNSM_E_ALIGNMENT;
+  if (E >= (1LL << 31) - L::TM) return FNSM_E_UNSUPPORTED;
+  if (L::SMEM_P > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
   const long long ntiles = (E + L::TM - 1) / L::TM;
   const long long need = (ntiles + L::GROUPS - 1) / L::GROUPS;
   const unsigned grid = (unsigned)(di.sms < need ? di.sms : need);
-  if (int rc = set_smem(k_div_tc32<ND>, L::SMEM)) return rc;
-  k_div_tc32<ND><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, D, E);
+  DivTCMaps maps{};
+  const bool tma = !force_plain && E % 4 == 0 && aligned16(u) && aligned16(out) &&
+                   map32_slabs_box(&maps.in, u, E, ND, 3, L::TM / 4) && map32_rows_box(&maps.out, out, E, ND, L::TM / 4);
+  if (tma) {
+    if (int rc = set_smem(k_div_tc32<ND, true>, L::SMEM)) return rc;
+    k_div_tc32<ND, true><<<grid, L::THREADS, L::SMEM, st>>>(maps, J, D, u, out, E);
+  } else {
+    if (int rc = set_smem(k_div_tc32<ND, false>, L::SMEM_P)) return rc;
+    k_div_tc32<ND, false><<<grid, L::THREADS, L::SMEM_P, st>>>(maps, J, D, u, out, E);
+  }
   return post_launch();
 }
 
 template <int ND, int NFD>
 static int launch_tc32_order(int kind, const float* J, const float* O, const OpmatRows& rows, int nrows, long long E,
-                             const DevInfo& di, cudaStream_t st) {
-  if (kind == FNSM_OP_LIFT_FE || kind == FNSM_OP_LIFT_EF) return launch_lift_tc32<ND, NFD>(kind, J, O, rows, nrows, E, di, st);
+                             const DevInfo& di, cudaStream_t st, bool force_plain) {
+  if (kind == FNSM_OP_LIFT_FE || kind == FNSM_OP_LIFT_EF)
+    return launch_lift_tc32<ND, NFD>(kind, J, O, rows, nrows, E, di, st, force_plain);
   // every row of a batched grad / div is its own launch; lift walks its fields inside one launch
   for (int r = 0; r < nrows; ++r) {
     const float* u = static_cast<const float*>(rows.field[r]);
     float* out = static_cast<float*>(rows.out[r]);
-    const int rc = kind == FNSM_OP_GRAD ? launch_grad_tc32<ND>(J, O, u, out, E, di, st)
-                                        : launch_div_tc32<ND>(J, O, u, out, E, di, st);
+    const int rc = kind == FNSM_OP_GRAD ? launch_grad_tc32<ND>(J, O, u, out, E, di, st, force_plain)
+                                        : launch_div_tc32<ND>(J, O, u, out, E, di, st, force_plain);
     if (rc) return rc;
   }
   return FNSM_OK;
 }
 
+// force_plain (cfg->reserved[0] bit 0, the same debug bit as the DMMA kernels): take the plain-producer
+// instantiation even when the operands qualify for TMA
 static int launch_tc32(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows,
-                       int ni, long long E, const DevInfo& di, cudaStream_t st) {
+                       int ni, long long E, const DevInfo& di, cudaStream_t st, bool force_plain = false) {
   const float* J = static_cast<const float*>(jac);
   const float* O = static_cast<const float*>(op);
   switch (ni) {
-    case 4: return launch_tc32_order<4, 3>(kind, J, O, rows, nrows, E, di, st);
-    case 10: return launch_tc32_order<10, 6>(kind, J, O, rows, nrows, E, di, st);
-    case 20: return launch_tc32_order<20, 10>(kind, J, O, rows, nrows, E, di, st);
-    case 35: return launch_tc32_order<35, 15>(kind, J, O, rows, nrows, E, di, st);
+    case 4: return launch_tc32_order<4, 3>(kind, J, O, rows, nrows, E, di, st, force_plain);
+    case 10: return launch_tc32_order<10, 6>(kind, J, O, rows, nrows, E, di, st, force_plain);
+    case 20: return launch_tc32_order<20, 10>(kind, J, O, rows, nrows, E, di, st, force_plain);
+    case 35: return launch_tc32_order<35, 15>(kind, J, O, rows, nrows, E, di, st, force_plain);
     default: return FNSM_E_UNSUPPORTED;
   }
 }

@@ -121,15 +121,37 @@ def test_opmat_fp32_orders_without_tensor_kernel(cq):
     check(E.grad(dtype="float32", ndof=20), 1001, cq)        # n % 4 != 0: the generic kernel takes any n
 
 
-@pytest.mark.parametrize("n", [1, 17, 1001])
+@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 127, 129, 1001, 10007, 75776 + 5, 200001, 200002])
 @pytest.mark.parametrize("builder", [E.grad, E.div, E.lift_ef, E.lift_fe])
-def test_opmat_fp32_auto_falls_back_when_tma_ineligible(cq, n, builder):
-    # n % 4 != 0: rows are not 16-byte multiples -> auto takes the mma.sync kernel's plain-load path,
-    # an explicit variant 3 reports the alignment error instead of silently running something else
+def test_opmat_fp32_tcgen05_plain_producer(cq, n, builder, variant):
+    """n % 4 != 0: rows are not 16-byte multiples, no tensor map can describe the operands.  Round 1 fell back to
+    the mma.sync kernels here (63-77 % of roofline); now the tcgen05 kernels themselves run with a cp.async producer
+    and plain vector stores (TMA = false instantiation), for auto and for an explicit variant 3 alike.  Sizes cover
+    a single ragged tile, tile boundaries +-1, two full rounds of tiles + 5 and several tiles per group."""
+    check(builder(dtype="float32"), n, cq, variant=variant)
+
+
+@pytest.mark.parametrize("order", [(4, 3), (10, 6), (20, 10)])
+def test_opmat_fp32_tcgen05_plain_producer_other_orders(cq, order):
+    nd, nfd = order
+    for n in (1, 1001, 10007, 200001):
+        check(E.grad(dtype="float32", ndof=nd), n, cq, variant=3)
+        check(E.div(dtype="float32", ndof=nd), n, cq, variant=3)
+        check(E.lift_fe(dtype="float32", nvol=nd, nfd=nfd), n, cq, variant=3)
+        check(E.lift_ef(dtype="float32", nvol=nd, nfd=nfd, b=3), n, cq, variant=3)
+
+
+@pytest.mark.parametrize("n", [1000, 10008])
+@pytest.mark.parametrize("builder", [E.grad, E.div, E.lift_ef, E.lift_fe])
+def test_opmat_fp32_tcgen05_plain_producer_forced_on_aligned_operands(cq, n, builder):
+    # flags bit 0 forces the plain producer where TMA would qualify: both instantiations must agree bit for bit
     e = builder(dtype="float32")
-    check(e, n, cq)
-    with pytest.raises(f.CudaBackendError):
-        check(e, n, cq, variant=3)
+    ins = np_oracle.generate_input_arrays(e, n, 9)
+    a = run(e, ins, cq, variant=3)
+    b = run(e, ins, cq, variant=3, flags=1)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
 
 
 @pytest.mark.parametrize("variant", [1, 3])
@@ -150,8 +172,9 @@ def test_fp32_tensor_path_accuracy_margin(cq, variant):
 @pytest.mark.parametrize("builder", [E.grad, E.div, E.lift_fe, E.lift_ef])
 def test_misaligned_operands_take_the_plain_path(cq, builder, dtype):
     """Operands that are views at an odd offset into a larger allocation (bases not 16-byte aligned)
-    rule out every TMA tensor map: auto must fall back (DMMA plain-load path / mma.sync kernel) and still
-    match the oracle; outputs are views at an odd offset as well."""
+    rule out every TMA tensor map: auto takes the plain producers (fp64: DMMA kernels with plain loads; fp32:
+    tcgen05 kernels with cp.async loads and vector stores, slabs shifted by the misalignment) and still matches
+    the oracle; outputs are views at an odd offset as well."""
     import torch
 
     e = builder(dtype=dtype)
@@ -159,9 +182,10 @@ def test_misaligned_operands_take_the_plain_path(cq, builder, dtype):
     ins = np_oracle.generate_input_arrays(e, n, 11)
     tdt = torch.float64 if dtype == "float64" else torch.float32
     dev = {}
-    for k, v in ins.items():
-        flat = torch.zeros(v.size + 3, dtype=tdt, device=cq.torch_device)
-        view = flat[1:1 + v.size].view(v.shape)          # base + one element: 8 / 4 bytes off a 16-byte boundary
+    for pos, (k, v) in enumerate(ins.items()):
+        off = 1 + (pos % 3 if dtype == "float32" else 0)   # fp32: 4, 8 and 12 bytes off a 16-byte boundary
+        flat = torch.zeros(v.size + 8, dtype=tdt, device=cq.torch_device)
+        view = flat[off:off + v.size].view(v.shape)        # base + 1..3 elements
         view.copy_(torch.from_numpy(np.ascontiguousarray(v)))
         assert view.data_ptr() % 16 != 0 and view.is_contiguous()
         dev[k] = view

@@ -5,7 +5,12 @@ DMMA kernels (TMA and plain-load producers), the generic DMMA / TF32 kernels, th
 mma.sync kernels, simt, tensor-product, generic and the wave operator.  ``FNSM_B200_MAX_SMS=6`` shrinks every
 persistent grid so each warp walks many work items: the mbarrier phase flips, slot re-arming and stage reuse
 that only show after the first item are all exercised.  Logs go to ``gpurun_out/sanitizer_<tool>.log``
-(copied to ``profiles/`` per round)."""
+(copied to ``profiles/`` per round).
+
+When the pool's ``compute-sanitizer`` wrapper refuses to run (round 2: closed pool-wide), the tool tests skip and
+``test_target_runs_clean_without_sanitizer`` carries the check the pool recommends instead: the same many-items-
+per-warp launches with canary guard zones around every buffer (out-of-bounds writes), and every result compared
+with the simt kernel of the same einsum (races on the slots / stages / barriers show up as wrong numbers)."""
 
 import os
 import shutil
@@ -20,10 +25,7 @@ TARGET = os.path.join(ROOT, "tools", "sanitize_target")
 
 
 def _sanitizer():
-    for cand in (shutil.which("compute-sanitizer"), "/usr/local/cuda/bin/compute-sanitizer"):
-        if cand and os.path.exists(cand):
-            return cand
-    return None
+    return shutil.which("compute-sanitizer")     # whatever the pool puts on PATH (it may be a policy wrapper)
 
 
 def _run(tool, families, extra=()):
@@ -41,6 +43,11 @@ def _run(tool, families, extra=()):
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"sanitizer_{tool}.log"), "a") as fh:
         fh.write("$ " + " ".join(cmd) + "\n" + out + "\n")
+    if "closed on this pool" in out:
+        # the pool's wrapper refuses to run the tool (observed round 2: "compute-sanitizer is closed on this pool
+        # and stays closed ... find a bad access with bounds checks and asserts of your own, small cases, and a
+        # comparison with the CPU reference") -> test_target_runs_clean_without_sanitizer is that check
+        pytest.skip("compute-sanitizer is closed on this GPU pool")
     return res.returncode, out
 
 
@@ -55,7 +62,10 @@ def test_target_runs_clean_without_sanitizer():
     res = subprocess.run([TARGET, *ALL], capture_output=True, text=True,
                          env=dict(os.environ, FNSM_B200_MAX_SMS="6"), timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert "MISMATCH" not in res.stdout
+    assert "MISMATCH" not in res.stdout and "GUARD VIOLATION" not in res.stdout + res.stderr
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "sanitize_target_plain.log"), "w") as fh:
+        fh.write(res.stdout)
 
 
 def test_memcheck():

@@ -21,17 +21,31 @@
 static unsigned long long g_seed = 0x9E3779B97F4A7C15ull;
 static double rnd() { g_seed = g_seed * 6364136223846793005ull + 1442695040888963407ull; return (double)(g_seed >> 11) * (1.0 / 9007199254740992.0); }
 
+// Device buffer with canary zones in front of and behind the payload (compute-sanitizer is closed on this
+// pool, so out-of-bounds WRITES are caught here: every guard byte must still hold the canary afterwards) and an
+// optional offset that makes the base not 16-byte aligned.
+static int g_guard_fail = 0;
 template <class T> struct Buf {
-  T* d = nullptr; size_t n = 0; size_t off = 0;
-  // `off` elements of slack in front: a non-zero value gives a base that is not 16-byte aligned
+  static constexpr size_t G = 1024;          // guard elements on each side
+  T* d = nullptr; T* raw = nullptr; size_t n = 0; size_t off = 0;
   Buf(size_t n_, bool random, size_t off_ = 0) : n(n_), off(off_) {
-    T* raw; CK(cudaMalloc(&raw, (n + off + 4) * sizeof(T)));
-    d = raw + off;
+    CK(cudaMalloc(&raw, (n + off + 2 * G) * sizeof(T)));
+    CK(cudaMemset(raw, 0xA5, (n + off + 2 * G) * sizeof(T)));
+    d = raw + G + off;
     std::vector<T> h(n);
     for (auto& v : h) v = random ? (T)rnd() : (T)0;
     CK(cudaMemcpy(d, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
   }
-  ~Buf() { cudaFree(d - off); }
+  ~Buf() {
+    std::vector<unsigned char> g((G + off) * sizeof(T)), t(G * sizeof(T));
+    CK(cudaMemcpy(g.data(), raw, g.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(t.data(), d + n, t.size(), cudaMemcpyDeviceToHost));
+    size_t bad = 0;
+    for (unsigned char c : g) bad += c != 0xA5;
+    for (unsigned char c : t) bad += c != 0xA5;
+    if (bad) { std::fprintf(stderr, "GUARD VIOLATION: %zu canary bytes overwritten around a %zu-element buffer\n", bad, n); g_guard_fail = 1; }
+    cudaFree(raw);
+  }
   std::vector<T> host() const { std::vector<T> h(n); CK(cudaMemcpy(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost)); return h; }
 };
 
@@ -96,23 +110,34 @@ static void generic(long long E) {
   std::printf("%-44s E=%-7lld ok\n", "generic eij,ej->ei", E);
 }
 
-static void wave(long long E, int dtype) {
-  const size_t sz = dtype == FNSM_F64 ? 8 : 4;
-  auto mk = [&](size_t n, bool rnd_) -> void* {
-    void* p; CK(cudaMalloc(&p, n * sz));
-    if (dtype == FNSM_F64) { std::vector<double> h(n); for (auto& v : h) v = rnd_ ? rnd() : 0; CK(cudaMemcpy(p, h.data(), n * sz, cudaMemcpyHostToDevice)); }
-    else { std::vector<float> h(n); for (auto& v : h) v = rnd_ ? (float)rnd() : 0; CK(cudaMemcpy(p, h.data(), n * sz, cudaMemcpyHostToDevice)); }
-    return p;
-  };
+template <class T>
+static void wave_t(long long E, int dtype) {
+  Buf<T> J(9 * E, true), D(3 * 35 * 35, true), v(3 * E * 35, true), u(E * 35, true), L(35 * 60, true), Jf(4 * E, true);
+  Buf<T> dv(E * 35, false), gr(3 * E * 35, false);
+  std::vector<Buf<T>*> F, lo;
   fnsm_wave_args a; std::memset(&a, 0, sizeof a);
-  a.J = mk(9 * E, true); a.D = mk(3 * 35 * 35, true); a.v = mk(3 * E * 35, true); a.u = mk(E * 35, true);
-  a.L = mk(35 * 60, true); a.Jface = mk(4 * E, true);
-  for (int k = 0; k < 4; ++k) { a.F[k] = mk(4 * E * 15, true); a.lift_out[k] = mk(E * 35, false); }
-  a.div_out = mk(E * 35, false); a.grad_out = mk(3 * E * 35, false);
+  a.J = J.d; a.D = D.d; a.v = v.d; a.u = u.d; a.L = L.d; a.Jface = Jf.d; a.div_out = dv.d; a.grad_out = gr.d;
+  for (int k = 0; k < 4; ++k) { F.push_back(new Buf<T>(4 * E * 15, true)); lo.push_back(new Buf<T>(E * 35, false)); a.F[k] = F[k]->d; a.lift_out[k] = lo[k]->d; }
   FN(fnsm_b200_wave3d_fused(dtype, &a, E, nullptr, nullptr));
+  // reference: the three einsums one by one through the simt kernels
+  fnsm_cfg ref; std::memset(&ref, 0, sizeof ref); ref.variant = 2;
+  Buf<T> dv2(E * 35, false), gr2(3 * E * 35, false);
+  std::vector<Buf<T>*> lo2; std::vector<const void*> fp; std::vector<void*> op2;
+  for (int k = 0; k < 4; ++k) { lo2.push_back(new Buf<T>(E * 35, false)); fp.push_back(F[k]->d); op2.push_back(lo2[k]->d); }
+  const void* f1[1] = {v.d}; void* o1[1] = {dv2.d};
+  FN(fnsm_b200_opmat_batch(FNSM_OP_DIV, dtype, J.d, D.d, f1, o1, 1, 3, 35, 35, E, &ref, nullptr));
+  const void* f2[1] = {u.d}; void* o2[1] = {gr2.d};
+  FN(fnsm_b200_opmat_batch(FNSM_OP_GRAD, dtype, J.d, D.d, f2, o2, 1, 3, 35, 35, E, &ref, nullptr));
+  FN(fnsm_b200_opmat_batch(FNSM_OP_LIFT_FE, dtype, Jf.d, L.d, fp.data(), op2.data(), 4, 4, 35, 15, E, &ref, nullptr));
   CK(cudaDeviceSynchronize());
-  std::printf("%-44s E=%-7lld ok\n", dtype == FNSM_F64 ? "wave_3d_p4 fp64" : "wave_3d_p4 fp32", E);
+  double worst = std::fmax(max_rel(dv.host(), dv2.host()), max_rel(gr.host(), gr2.host()));
+  for (int k = 0; k < 4; ++k) worst = std::fmax(worst, max_rel(lo[k]->host(), lo2[k]->host()));
+  const double tol = sizeof(T) == 8 ? 1e-13 : 1e-5;
+  std::printf("%-44s E=%-7lld            max rel diff vs simt %.3g %s\n", sizeof(T) == 8 ? "wave_3d_p4 fp64" : "wave_3d_p4 fp32", E, worst, worst < tol ? "ok" : "MISMATCH");
+  if (!(worst < tol)) g_fail = 1;
+  for (int k = 0; k < 4; ++k) { delete F[k]; delete lo[k]; delete lo2[k]; }
 }
+static void wave(long long E, int dtype) { if (dtype == FNSM_F64) wave_t<double>(E, dtype); else wave_t<float>(E, dtype); }
 
 int main(int argc, char** argv) {
   std::vector<std::string> fams;
@@ -150,7 +175,7 @@ int main(int argc, char** argv) {
       opmat<float>("tf32_gen grad p3", FNSM_OP_GRAD, 20, 10, 9001, 1, 1, 0);
       opmat<float>("tf32_gen lift_fe p2 b=4", FNSM_OP_LIFT_FE, 10, 6, 9001, 1, 4, 0);
     } else if (f == "simt") {
-      opmat<double>("simt grad 2-D p4 (15 dofs)", FNSM_OP_GRAD, 15, 5, 3001, 2, 1, 0);
+      opmat<double>("simt grad 15 dofs", FNSM_OP_GRAD, 15, 5, 3001, 2, 1, 0);
       opmat<float>("simt div p5 (56 dofs)", FNSM_OP_DIV, 56, 21, 1001, 2, 1, 0);
     } else if (f == "tp") {
       tensor_product(3001);
@@ -165,5 +190,6 @@ int main(int argc, char** argv) {
     }
   }
   std::printf("launches through the ABI: %lld\n", (long long)fnsm_b200_launch_count());
-  return g_fail;
+  if (g_guard_fail) std::printf("GUARD VIOLATION\n");
+  return g_fail | (g_guard_fail << 1);
 }
