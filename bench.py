@@ -63,6 +63,10 @@ WORKLOADS = {
     "lift_p4_f32": ("DG face-mass lift ifj,fe,fej->ei b=4 p=4 tets fp32", 4_000_000, "configs[2] einsum in fp32"),
     "wave_p4": ("wave_3d_p4 operator: div(v) + grad(u) + 4-field lift in one call, fp64", 4_000_000, "configs[3] fp64"),
     "wave_p4_f32": ("wave_3d_p4 operator: div(v) + grad(u) + 4-field lift in one call, fp32", 4_000_000, "configs[3] fp32"),
+    "se_p4": ("div components se,sij,ej->ei: 3 rows J_b(3,E) R(3,35,35) u_b(E,35) p=4 tets fp64 (shared operator)",
+              4_000_000, "SURVEY 8(f3); reference test/test_codegen.py:34-60"),
+    "se_face_p4": ("face mass se,sij,ej->ei: 4 rows J(4,E) R(4,15,15) v_k(E,15) fp64 (shared operator)",
+                   4_000_000, "SURVEY 8(f3); reference test/test_codegen.py:63-88"),
     "hexd_p7": ("fused hex derivative eabc,ia->eibc + eabc,ib->eaic + eabc,ic->eabi p=7 fp64 (A read once)",
                 4_000_000, "SURVEY 8(f3)"),
 }
@@ -80,6 +84,10 @@ SUITE = [
     ("grad_p4", None, False), ("lift_p4", None, False), ("wave_p4", None, False),
     ("wave_p4_f32", None, False), ("tp_p7", None, False),
     ("grad_p4_f32", None, False), ("div_p4_f32", None, False), ("lift_p4_f32", None, False),
+    # shared-operator families on the tensor path; the alignment cliff (odd E / E % 4 != 0)
+    ("se_p4", None, False), ("se_face_p4", None, False),
+    ("div_p4", 4_000_001, False), ("lift_p4", 4_000_001, False),
+    ("div_p4_f32", 4_000_001, False), ("lift_p4_f32", 4_000_002, False),
 ]
 STRONG_SUITE = ["div_p4", "wave_p4", "tp_p7"]
 
@@ -102,6 +110,12 @@ def build_einsum(name: str):
             "ifj,fe,fej->ei",
             [[f.array("L", (nd, 4, nfd), dt), f.array("Jface", (4, "E"), dt),
               f.array(f"F_{k}", (4, "E", nfd), dt)] for k in range(4)])
+    if base == "se_p4":
+        return f.batched_einsum("se,sij,ej->ei", [[f.array(f"J{c}", (3, "E"), dt), f.array("R", (3, 35, 35), dt),
+                                                   f.array(f"u{c}", ("E", 35), dt)] for c in "xyz"])
+    if base == "se_face_p4":
+        return f.batched_einsum("se,sij,ej->ei", [[f.array("J", (4, "E"), dt), f.array("R", (4, 15, 15), dt),
+                                                   f.array(f"v{k}", ("E", 15), dt)] for k in range(4)])
     if base == "tp_p7":
         return f.einsum("eabc,ia->eibc", f.array("A", ("E", 8, 8, 8), dt), f.array("M", (8, 8), dt))
     if base in ("wave_p4", "hexd_p7"):

@@ -18,13 +18,15 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfnsm_b20
 
 FNSM_F64, FNSM_F32, FNSM_I32, FNSM_I64, FNSM_C64, FNSM_C128 = range(6)
 OP_GRAD, OP_DIV, OP_LIFT_EF, OP_LIFT_FE = 0, 1, 2, 3
-K_GENERIC, K_GRAD, K_DIV, K_LIFT, K_WAVE3D, K_TENSOR_PRODUCT = range(6)
+K_GENERIC, K_GRAD, K_DIV, K_LIFT, K_WAVE3D, K_TENSOR_PRODUCT, K_SE, K_HEX_DERIV = range(8)
 MAX_INDICES, MAX_OPERANDS = 12, 6
 E_BAD_CONFIG = -3
 
 EXPORTED_SYMBOLS = (
     "fnsm_b200_generic_einsum",
     "fnsm_b200_opmat_batch",
+    "fnsm_b200_opmat_se",
+    "fnsm_b200_opmat_se_supported",
     "fnsm_b200_wave3d_fused",
     "fnsm_b200_tensor_product",
     "fnsm_b200_query_cfg_space",
@@ -100,6 +102,8 @@ def lib() -> C.CDLL:
     handle.fnsm_b200_generic_einsum.argtypes = [C.POINTER(EinsumDesc), i32, pvp, pvp, vp]
     handle.fnsm_b200_opmat_batch.argtypes = [
         i32, i32, vp, vp, pvp, pvp, i32, i32, i32, i32, i64, C.POINTER(Cfg), vp]
+    handle.fnsm_b200_opmat_se.argtypes = [i32, i32, pvp, vp, pvp, pvp, i32, i32, i32, i32, i64, C.POINTER(Cfg), vp]
+    handle.fnsm_b200_opmat_se_supported.argtypes = [i32, i32, i32, i32]
     handle.fnsm_b200_wave3d_fused.argtypes = [i32, C.POINTER(WaveArgs), i64, C.POINTER(Cfg), vp]
     handle.fnsm_b200_tensor_product.argtypes = [i32, vp, vp, vp, i32, i32, i64, C.POINTER(Cfg), vp]
     handle.fnsm_b200_query_cfg_space.argtypes = [i32, C.POINTER(CfgRange), i32]

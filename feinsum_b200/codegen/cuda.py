@@ -28,6 +28,7 @@ kernel_id          subscripts (up to renaming)   C ABI
 ``div``            ``xre,rij,xej->ei``           ``fnsm_b200_opmat_batch``
 ``lift_ef``        ``ef,fij,fej->ei``            ``fnsm_b200_opmat_batch``
 ``lift_fe``        ``ifj,fe,fej->ei``            ``fnsm_b200_opmat_batch``
+``opmat_se``       ``se,sij,ej->ei``             ``fnsm_b200_opmat_se``
 ``tensor_product`` ``eabc,ia->eibc`` (+2 modes)  ``fnsm_b200_tensor_product``
 ``generic``        anything else                 ``fnsm_b200_generic_einsum``
 =================  ============================  ===============================
@@ -121,6 +122,16 @@ _OPMAT_PATTERNS = (
     ("lift_fe", "ifj,fe,fej->ei", _cabi.OP_LIFT_FE),
 )
 _TP_PATTERNS = ("eabc,ia->eibc", "eabc,ib->eaic", "eabc,ic->eabi")
+#: shared-operator family (reference test/test_codegen.py:34-88; tuning/impls/re_rij_ej_to_ei*.py)
+#: J(S,E) as in test/test_codegen.py:34-88, or J(E,S) as in examples/dg_wave_div.py:14
+_SE_PATTERNS = ("se,sij,ej->ei", "es,sij,ej->ei")
+
+
+def se_kernel_available(dt: np.dtype[Any], n_s: int, n_i: int, n_j: int) -> bool:
+    """Mirror of ``se_supported`` in ``csrc/opmat_se.cuh`` (checked against the library in tests/test_cabi.py)."""
+    if dt != np.dtype("float64") or n_i != n_j:
+        return False
+    return (n_s == 3 and n_i in (4, 10, 20, 35)) or (n_s == 4 and n_i in (3, 6, 10, 15))
 
 
 def _uniform_dtype(einsum: BatchedEinsum) -> np.dtype[Any] | None:
@@ -217,6 +228,19 @@ def classify(einsum: BatchedEinsum) -> KernelPlan:
                 ),
                 e,
             )
+        for es_layout, pattern in enumerate(_SE_PATTERNS if einsum.n == 3 else ()):
+            m = match_subscripts(einsum, pattern)
+            if m is None:
+                continue
+            perm, imap = m
+            others = [imap[k] for k in imap if k != "e"]
+            ns, ni, nj = (_int_extent(einsum, imap[k]) for k in "sij")
+            # the operator is shared by all rows; J and the field may differ from row to row
+            op_shared = len({row[perm[1]].name for row in einsum.args}) == 1
+            if (_is_long(einsum, imap["e"]) and not any(_is_long(einsum, o) for o in others) and op_shared
+                    and se_kernel_available(dt, int(ns), int(ni), int(nj))):  # type: ignore[arg-type]
+                return KernelPlan("opmat_se", perm,
+                                  Map(n_s=int(ns), n_i=int(ni), n_j=int(nj), es=es_layout), imap["e"])  # type: ignore[arg-type]
         if einsum.n == 2:
             for mode, pattern in enumerate(_TP_PATTERNS):
                 m = match_subscripts(einsum, pattern)
@@ -479,6 +503,25 @@ class CudaExecutor:
                     _cabi.check(rc, f"fnsm_b200_opmat_batch[{kid}]")
 
             return launch
+        if kid == "opmat_se":
+            perm = self.plan.perm
+            b = es.b
+            jacs = (C.c_void_p * b)(*[ins[row[perm[0]].name].data_ptr() for row in es.args])
+            op = ins[es.args[0][perm[1]].name]
+            fields = (C.c_void_p * b)(*[ins[row[perm[2]].name].data_ptr() for row in es.args])
+            out_ptrs = (C.c_void_p * b)(*[outs[n].data_ptr() for n in self.output_names])
+            E = sizes[es.index_to_dim_length[self.plan.long_index].name]  # type: ignore[union-attr]
+            f = self.plan.facts
+            se_args = (_DTYPE_CODE[self.out_dtypes[0]], f["es"], jacs, C.c_void_p(op.data_ptr()), fields, out_ptrs, b,
+                       f["n_s"], f["n_i"], f["n_j"], C.c_int64(E), self._cfg, stream)
+            se_fn = self.lib.fnsm_b200_opmat_se
+
+            def launch_se() -> None:
+                rc = se_fn(*se_args)
+                if rc:
+                    _cabi.check(rc, "fnsm_b200_opmat_se")
+
+            return launch_se
         if kid == "tensor_product":
             perm = self.plan.perm
             E = sizes[es.index_to_dim_length[self.plan.long_index].name]  # type: ignore[union-attr]

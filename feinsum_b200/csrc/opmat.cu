@@ -12,6 +12,7 @@
 #include "opmat_tc32.cuh"
 #include "opmat_dmma_gen.cuh"
 #include "opmat_tf32_gen.cuh"
+#include "opmat_se.cuh"
 #include <cstdio>
 #include <cstring>
 
@@ -166,4 +167,22 @@ extern "C" int fnsm_b200_wave3d_fused(int32_t dtype, const fnsm_wave_args* a, in
   rc = opmat_dispatch(FNSM_OP_GRAD, dtype, a->J, a->D, f2, o2, 1, 3, 35, 35, E, cfg, st);
   if (rc) return rc;
   return opmat_dispatch(FNSM_OP_LIFT_FE, dtype, a->Jface, a->L, a->F, a->lift_out, 4, 4, 35, 15, E, cfg, st);
+}
+
+extern "C" int fnsm_b200_opmat_se(int32_t dtype, int32_t jac_layout, const void* const* jacs, const void* op,
+                                  const void* const* fields, void* const* outs, int32_t b,
+                                  int32_t n_s, int32_t n_i, int32_t n_j, int64_t E,
+                                  const fnsm_cfg* cfg, void* stream) {
+  using namespace fnsm;
+  if (!jacs || !op || !fields || !outs || b <= 0 || E < 0) return FNSM_E_BAD_ARG;
+  if (n_s < 1 || n_i < 1 || n_j < 1 || jac_layout < 0 || jac_layout > 1) return FNSM_E_BAD_ARG;
+  if (cfg && (cfg->variant < 0 || cfg->variant > 3)) return FNSM_E_BAD_CONFIG;
+  if (E == 0) return FNSM_OK;
+  DevInfo di;
+  if (int rc = device_info(&di)) return rc;
+  return launch_se(dtype, jac_layout, jacs, op, fields, outs, b, n_s, n_i, n_j, E, cfg, di, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fnsm_b200_opmat_se_supported(int32_t dtype, int32_t n_s, int32_t n_i, int32_t n_j) {
+  return fnsm::se_supported(dtype, n_s, n_i, n_j) ? 1 : 0;
 }

@@ -213,39 +213,53 @@ struct WorkQueue {
 // ================================================================= DIV =====
 // out[e,i] = sum_{r,j} D[r,i,j] * w[r,e,j],   w[r,e,j] = sum_x J[x,r,e] u[x,e,j]
 // k-tiles ordered (jq, r): kt = 3*jq + r, k-in-tile t <-> j = 4*jq + t
-struct DivLayout {
+// NX = 3: the divergence.  NX = 1: the same kernel without the x-sum, w[r,e,j] = J[r,e] u[e,j] -- the shared-operator
+// family  se,sij,ej->ei  (reference test/test_codegen.py:34-88 "div components" / tuning/impls/re_rij_ej_to_ei*.py),
+// which is  xse,sij,xej->ei  with |x| = 1: J(3,E), u(E,35).
+template <int NX>
+struct DivLayoutT {
   static constexpr int KT = 27;
   static constexpr int B_MAIN = KT * kNT * 32;                       // 3456
   static constexpr int B_LEFT = KT * 4 * 4;                          // [kt][t][3 dofs + pad]
   static constexpr int B_DOUBLES = B_MAIN + B_LEFT;                  // 3888
   static constexpr int U_SLAB = kCH * 35;                            // doubles per x
-  static constexpr int SLOT_DOUBLES = 3 * U_SLAB + 9 * kCH;          // 1824 -> 14592 B
+  static constexpr int SLOT_DOUBLES = NX * U_SLAB + 3 * NX * kCH;    // NX = 3: 1824 -> 14592 B
   static constexpr uint32_t SLOT_BYTES = SLOT_DOUBLES * 8;
 };
+using DivLayout = DivLayoutT<3>;
 
+// ES (NX = 1 only): the geometric factors are laid out J(E, 3) -- "es,sij,ej->ei", reference
+// examples/dg_wave_div.py:14 -- instead of J(3, E); the slot then holds them as [el][s]
+template <int NX, bool ES = false>
 __device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps* maps,
                                           const double* __restrict__ Jg, const double* __restrict__ ug,
                                           long long chunk, long long E, bool tma, int lane) {
-  using L = DivLayout;
+  using L = DivLayoutT<NX>;
   const long long e0 = chunk * kCH;
   if (tma) {
     if (elect_one()) {
       fence_proxy_async();
       mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
-      tma_load_3d(s, &maps->in, 0, (int)(chunk * (kCH / 2)), 0, bar);          // u[0..2][16 el][35]
-      tma_load_2d(s + 3 * L::U_SLAB, &maps->jac, (int)e0, 0, bar);              // J[9][16 el]
+      if (NX == 3) tma_load_3d(s, &maps->in, 0, (int)(chunk * (kCH / 2)), 0, bar);   // u[0..2][16 el][35]
+      else         tma_load_2d(s, &maps->in, 0, (int)(chunk * (kCH / 2)), bar);      // u[16 el][35]
+      if (ES) tma_load_2d(s + NX * L::U_SLAB, &maps->jac, 0, (int)(chunk * (kCH / 2)), bar);   // J[16 el][3]
+      else    tma_load_2d(s + NX * L::U_SLAB, &maps->jac, (int)e0, 0, bar);      // J[3 NX][16 el]
     }
   } else {
     // rows of elements past E are not copied: they hold stale (finite or not) data, are computed -- the rows of a
     // DMMA tile are independent -- and never stored
     const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-    for (int x = 0; x < 3; ++x) {
+    for (int x = 0; x < NX; ++x) {
       const double* src = ug + ((long long)x * E + e0) * 35;
       for (int k = lane; k < ne * 35; k += 32) cp_async8(s + x * L::U_SLAB + k, src + k);
     }
-    for (int k = lane; k < 9 * kCH; k += 32) {
-      const int xr = k / kCH, el = k - xr * kCH;
-      if (el < ne) cp_async8(s + 3 * L::U_SLAB + k, Jg + (long long)xr * E + e0 + el);
+    for (int k = lane; k < 3 * NX * kCH; k += 32) {
+      if (ES) {
+        if (k < 3 * ne) cp_async8(s + NX * L::U_SLAB + k, Jg + e0 * 3 + k);
+      } else {
+        const int xr = k / kCH, el = k - xr * kCH;
+        if (el < ne) cp_async8(s + NX * L::U_SLAB + k, Jg + (long long)xr * E + e0 + el);
+      }
     }
     cp_async_arrive_noinc(bar);
   }
@@ -257,11 +271,11 @@ __device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps
 // memory for two more warps (19 KB per warp staged -> 10 warps, 14.6 KB direct -> 12 warps)
 // DBG (profiling aid, results invalid): 1 = no conversion (A fragments = constants), 2 = no left-over
 // DFMAs, 4 = no epilogue
-template <int NW, bool STAGED, int DBG = 0>
+template <int NW, bool STAGED, int DBG = 0, int NX = 3, bool ES = false>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, const double* __restrict__ Dg,
            const double* __restrict__ ug, double* __restrict__ outg, long long E, int flags) {
-  using L = DivLayout;
+  using L = DivLayoutT<NX>;
   release_dependent_kernels();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sB = reinterpret_cast<double*>(smem_raw);
@@ -282,14 +296,14 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   double* s = slots + (size_t)warp * L::SLOT_DOUBLES;
   double* stage = stages + (size_t)warp * (STAGED ? OUT_BLOCK : 0);
   uint64_t* bar = &bars[warp];
-  const double* sJ = s + 3 * L::U_SLAB;
+  const double* sJ = s + NX * L::U_SLAB;
   const long long nchunks = (E + kCH - 1) / kCH;
   const WorkQueue wq{work_ctr, nchunks};
   const int g = lane >> 2, t = lane & 3, tpad = t < 3 ? t : 2;
 
   const bool tma = flags & kFlagTma, dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
   long long cur = wq.take(lane), nxt = wq.take(lane);
-  if (cur < nchunks && !dbg_noload) div_issue(s, bar, &maps, Jg, ug, cur, E, tma, lane);
+  if (cur < nchunks && !dbg_noload) div_issue<NX, ES>(s, bar, &maps, Jg, ug, cur, E, tma, lane);
   // operator tables are staged while the first TMA loads are in flight
   // main operator fragments, column tiles in pairs so that one LDS.128 feeds two of them:
   // sB[((kt*2 + p)*32 + lane)*2 + h] = D[r][8(2p+h)+g][4jq+t]
@@ -321,24 +335,26 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
         continue;
       }
       const int el = chunk_el(g, m);
-      double Jr[9];
+      double Jr[3 * NX];
 #pragma unroll
-      for (int xr = 0; xr < 9; ++xr) Jr[xr] = sJ[xr * kCH + el];
+      for (int xr = 0; xr < 3 * NX; ++xr) Jr[xr] = ES ? sJ[el * 3 + xr] : sJ[xr * kCH + el];
 #pragma unroll
       for (int jq = 0; jq < 9; ++jq) {
         // k-slot j = 35 (jq = 8, t = 3) is padding: its operator entries are zero, so the lane reads j = 34 of its
         // own element there (finite whenever the element's data is) instead of paying a select per value
         const int j = jq == 8 ? 32 + tpad : 4 * jq + t;
-        double ux[3];
+        double ux[NX];
 #pragma unroll
-        for (int x = 0; x < 3; ++x) ux[x] = s[x * L::U_SLAB + el * 35 + j];
+        for (int x = 0; x < NX; ++x) ux[x] = s[x * L::U_SLAB + el * 35 + j];
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
-          a[m][3 * jq + r] = fma(Jr[6 + r], ux[2], fma(Jr[3 + r], ux[1], Jr[r] * ux[0]));
+        for (int r = 0; r < 3; ++r) {
+          if (NX == 3) a[m][3 * jq + r] = fma(Jr[2 * NX + r], ux[NX - 1], fma(Jr[NX + r], ux[NX > 1 ? 1 : 0], Jr[r] * ux[0]));
+          else         a[m][3 * jq + r] = Jr[r] * ux[0];
+        }
       }
     }
     __syncwarp();                                  // every lane is done reading the slot
-    if (nxt < nchunks && !dbg_noload) div_issue(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
+    if (nxt < nchunks && !dbg_noload) div_issue<NX, ES>(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
     const unsigned tk = wq.ticket(lane);          // ticket after next; its latency hides under the DMMAs
 
     // ---- DMMA stream ----

@@ -93,7 +93,9 @@ enum {
   FNSM_K_DIV = 2,
   FNSM_K_LIFT = 3,
   FNSM_K_WAVE3D = 4,
-  FNSM_K_TENSOR_PRODUCT = 5
+  FNSM_K_TENSOR_PRODUCT = 5,
+  FNSM_K_SE = 6,
+  FNSM_K_HEX_DERIV = 7
 };
 
 /* ------------------------------------------------------------------------
@@ -137,6 +139,25 @@ int fnsm_b200_opmat_batch(int32_t kind, int32_t dtype,
                           const void* const* fields, void* const* outs, int32_t b,
                           int32_t n_outer, int32_t n_i, int32_t n_j,
                           int64_t E, const fnsm_cfg* cfg, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Shared-operator family  se,sij,ej->ei :  out_b[e,i] = sum_{s,j} R[s,i,j] J_b[s,e] u_b[e,j]
+ * replaces: generate_loopy + tuning/impls/{re_rij_ej_to_ei*, re_rji_ej_to_ei_3d_cross_product_v0}.py
+ * (reference test/test_codegen.py:34-88: "div components" J{x,y,z}(3,E) R(3,35,35) u{x,y,z}(E,35),
+ *  "face mass" J(4,E) R(4,15,15) v_k(E,15)).
+ *   jac_layout 0: J_b(n_s, E)  "se,sij,ej->ei" (test/test_codegen.py:34-88);
+ *              1: J_b(E, n_s)  "es,sij,ej->ei" (examples/dg_wave_div.py:14, test/test_feinsum.py:42)
+ *   jacs     b device pointers J_b   (rows may share one array)
+ *   op       R(n_s, n_i, n_j), shared by all rows
+ *   fields   b device pointers u_b(E, n_j);  outs = b device pointers out_b(E, n_i)
+ * Compiled shapes: fnsm_b200_opmat_se_supported(dtype, n_s, n_i, n_j) != 0 (fp64; S = 3 with 4/10/20/35 dofs,
+ * S = 4 with 3/6/10/15 dofs); anything else returns FNSM_E_UNSUPPORTED and belongs to the generic kernel.
+ * ---------------------------------------------------------------------- */
+int fnsm_b200_opmat_se(int32_t dtype, int32_t jac_layout, const void* const* jacs, const void* op,
+                       const void* const* fields, void* const* outs, int32_t b,
+                       int32_t n_s, int32_t n_i, int32_t n_j, int64_t E,
+                       const fnsm_cfg* cfg, void* stream);
+int fnsm_b200_opmat_se_supported(int32_t dtype, int32_t n_s, int32_t n_i, int32_t n_j);
 
 /* ------------------------------------------------------------------------
  * wave_3d_p4: div(v) + grad(u) + 4-field face-mass lift behind ONE call on one

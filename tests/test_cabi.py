@@ -82,3 +82,16 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     finally:
         monkeypatch.undo()
         _cabi.lib.cache_clear()
+
+
+def test_se_shape_table_mirrors_the_library(lib):
+    import numpy as np
+
+    from feinsum_b200.codegen.cuda import se_kernel_available
+
+    for dt, code in ((np.dtype("float64"), _cabi.FNSM_F64), (np.dtype("float32"), _cabi.FNSM_F32)):
+        for ns in range(1, 6):
+            for ni in (3, 4, 6, 10, 15, 20, 35, 36):
+                for nj in (ni, ni + 1):
+                    assert bool(lib.fnsm_b200_opmat_se_supported(code, ns, ni, nj)) == \
+                        se_kernel_available(dt, ns, ni, nj), (dt, ns, ni, nj)

@@ -16,7 +16,7 @@ def test_named_families():
     for mode in range(3):
         p = classify(E.tensor_product(mode))
         assert p.kernel_id == "tensor_product" and p.facts["mode"] == mode and p.facts["n1d"] == 8
-    assert classify(E.div_components()).kernel_id == "generic"
+    assert classify(E.div_components()).kernel_id == "opmat_se"
     assert classify(E.matvec_f32()).kernel_id == "generic"
 
 
@@ -123,3 +123,26 @@ def test_wave3d_program_host_spec():
         conc = tuple(7 if isinstance(d, SizeParam) else d for d in s)
         assert conc == {**ins, **outs}[n]
     assert spec.in_shapes["D"] == (3, 35, 35) and spec.in_dtypes["J"] == np.dtype("float32")
+
+
+def test_shared_operator_family_se():
+    """se,sij,ej->ei (reference test/test_codegen.py:34-88): rows with their own J and u, one operator."""
+    p = classify(E.div_components())
+    assert p.kernel_id == "opmat_se" and dict(p.facts) == {"n_s": 3, "n_i": 35, "n_j": 35, "es": 0}
+    # J(E,3): the layout of reference examples/dg_wave_div.py:14 / test/test_feinsum.py:42
+    e = f.batched_einsum("es,sij,ej->ei", [[f.array(f"J{c}", ("E", 3)), f.array("R", (3, 35, 35)),
+                                            f.array(f"u{c}", ("E", 35))] for c in "xyz"])
+    assert dict(classify(e).facts)["es"] == 1
+    assert classify(E.face_mass_se()).kernel_id == "opmat_se"
+    # renamed, operands permuted
+    e = f.batched_einsum("aq,ra,rpq->ap", [[f.array(f"w{k}", ("N", 20)), f.array(f"G{k}", (3, "N")),
+                                            f.array("Op", (3, 20, 20))] for k in range(2)])
+    p = classify(e)
+    assert p.kernel_id == "opmat_se" and p.perm == (1, 2, 0)
+    # operator differs between rows / no compiled shape / fp32 -> generic
+    e = f.batched_einsum("se,sij,ej->ei", [[f.array("J", (3, "E")), f.array(f"R{k}", (3, 35, 35)),
+                                            f.array(f"u{k}", ("E", 35))] for k in range(2)])
+    assert classify(e).kernel_id == "generic"
+    e = f.einsum("se,sij,ej->ei", f.array("J", (5, "E")), f.array("R", (5, 7, 7)), f.array("u", ("E", 7)))
+    assert classify(e).kernel_id == "generic"
+    assert classify(E.div_components("float32")).kernel_id == "generic"

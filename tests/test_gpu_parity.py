@@ -401,3 +401,43 @@ def test_generic_rejects_mixed_row_dtypes(cq):
                                      [f.array("B", ("I", 4), "float32"), f.array("y", 4, "float32")]])
     with pytest.raises(NotImplementedError):
         generate_cuda(e).executor(cq)
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 100, 1001, 10007, 100000])
+@pytest.mark.parametrize("builder", [E.div_components, E.face_mass_se])
+def test_shared_operator_family_se(cq, builder, n):
+    """se,sij,ej->ei on the FP64 tensor path (reference test/test_codegen.py:34-88): div components = three rows with
+    their own J and u on the NX = 1 divergence kernel (TMA for even n, cp.async producer for odd n); face mass = four
+    rows sharing J on the warp-per-chunk kernel."""
+    assert generate_cuda(builder()).kernel_id == "opmat_se"
+    check(builder(), n, cq)
+
+
+@pytest.mark.parametrize("shape", [(3, 4), (3, 10), (3, 20), (4, 3), (4, 6), (4, 10)])
+def test_shared_operator_family_se_other_orders(cq, shape):
+    ns, nd = shape
+    e = f.batched_einsum("se,sij,ej->ei", [[f.array(f"J{k}", (ns, "E")), f.array("R", (ns, nd, nd)),
+                                            f.array(f"u{k}", ("E", nd))] for k in range(3)])
+    assert generate_cuda(e).kernel_id == "opmat_se"
+    for n in (1, 31, 32, 33, 1001, 20000):
+        check(e, n, cq)
+
+
+def test_shared_operator_family_se_many_rows_and_permuted_operands(cq):
+    e = f.batched_einsum("aq,ra,rpq->ap", [[f.array(f"w{k}", ("N", 35)), f.array(f"G{k % 2}", (3, "N")),
+                                            f.array("Op", (3, 35, 35))] for k in range(9)])   # 9 rows > one launch group
+    assert generate_cuda(e).kernel_id == "opmat_se"
+    check(e, 777, cq)
+    check(e, 778, cq)
+
+
+@pytest.mark.parametrize("n", [1, 16, 17, 1001, 10008])
+@pytest.mark.parametrize("shape", [(3, 35), (4, 15), (3, 10)])
+def test_shared_operator_family_es_layout(cq, shape, n):
+    # "es,sij,ej->ei": J(E,S) as in reference examples/dg_wave_div.py:14, test/test_feinsum.py:42
+    ns, nd = shape
+    e = f.batched_einsum("es,sij,ej->ei", [[f.array(f"J{c}", ("E", ns)), f.array("R", (ns, nd, nd)),
+                                            f.array(f"u{c}", ("E", nd))] for c in "xyz"])
+    plan = generate_cuda(e).plan
+    assert plan.kernel_id == "opmat_se" and plan.facts["es"] == 1
+    check(e, n, cq)
