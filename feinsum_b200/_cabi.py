@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = (
     "fnsm_b200_opmat_se_supported",
     "fnsm_b200_wave3d_fused",
     "fnsm_b200_tensor_product",
+    "fnsm_b200_hex_deriv",
     "fnsm_b200_query_cfg_space",
     "fnsm_b200_measure_peak",
     "fnsm_b200_copy2d_async",
@@ -106,6 +107,7 @@ def lib() -> C.CDLL:
     handle.fnsm_b200_opmat_se_supported.argtypes = [i32, i32, i32, i32]
     handle.fnsm_b200_wave3d_fused.argtypes = [i32, C.POINTER(WaveArgs), i64, C.POINTER(Cfg), vp]
     handle.fnsm_b200_tensor_product.argtypes = [i32, vp, vp, vp, i32, i32, i64, C.POINTER(Cfg), vp]
+    handle.fnsm_b200_hex_deriv.argtypes = [i32, vp, pvp, pvp, i32, i64, C.POINTER(Cfg), vp]
     handle.fnsm_b200_query_cfg_space.argtypes = [i32, C.POINTER(CfgRange), i32]
     handle.fnsm_b200_measure_peak.argtypes = [i32, C.POINTER(C.c_double)]
     handle.fnsm_b200_copy2d_async.argtypes = [vp, i64, vp, i64, i64, i64, i32, vp]

@@ -99,7 +99,8 @@ extern "C" int fnsm_b200_query_cfg_space(int32_t kernel_id, fnsm_cfg_range* out,
       set_range(&tmp[n++], "ctas_per_sm", 0, 8, 1, 0);
       break;
     case FNSM_K_HEX_DERIV:
-      set_range(&tmp[n++], "ctas_per_sm", 0, 64, 1, 0);
+      set_range(&tmp[n++], "ctas_per_sm", 0, 8, 1, 0);
+      set_range(&tmp[n++], "stages", 2, 4, 1, 3);
       break;
     case FNSM_K_GRAD: case FNSM_K_DIV: case FNSM_K_LIFT: case FNSM_K_WAVE3D:
       return fnsm::opmat_cfg_space(kernel_id, out, cap);

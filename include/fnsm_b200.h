@@ -194,6 +194,17 @@ int fnsm_b200_tensor_product(int32_t dtype, const void* A, const void* M, void* 
                              const fnsm_cfg* cfg, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Fused hex derivative: the three tensor-product modes applied to the SAME field,
+ *   outs[0] = eabc,ia->eibc (M[0])   outs[1] = eabc,ib->eaic (M[1])   outs[2] = eabc,ic->eabi (M[2])
+ * with A(E,n1d,n1d,n1d) read once: 16 KB instead of 24 KB of traffic per fp64 p = 7 element.
+ * M = 3 device pointers to (n1d, n1d) row-major operators (may be the same array), outs = 3 device pointers.
+ * Compiled for fp64, n1d = 8 (FNSM_E_UNSUPPORTED otherwise); A and outs 16-byte aligned.
+ * cfg->stages (2..4, default 3): elements in flight per warp; cfg->ctas_per_sm caps the persistent grid.
+ * ---------------------------------------------------------------------- */
+int fnsm_b200_hex_deriv(int32_t dtype, const void* A, const void* const* M, void* const* outs,
+                        int32_t n1d, int64_t E, const fnsm_cfg* cfg, void* stream);
+
+/* ------------------------------------------------------------------------
  * Tuning-space introspection (replaces the @transform_param declarations of a
  * transform script, reference tuning/__init__.py:109-194).  Writes up to `cap`
  * ranges, returns the number of tunables of the kernel (or a negative error).
