@@ -14,7 +14,9 @@ from typing import Any
 
 from feinsum_b200.diagnostics import CudaBackendError, InvalidParameterError
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfnsm_b200.so")
+#: FNSM_B200_LIB points the loader at another build of the library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("FNSM_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                           "libfnsm_b200.so")
 
 FNSM_F64, FNSM_F32, FNSM_I32, FNSM_I64, FNSM_C64, FNSM_C128 = range(6)
 OP_GRAD, OP_DIV, OP_LIFT_EF, OP_LIFT_FE = 0, 1, 2, 3

@@ -130,6 +130,30 @@ __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 lanes
 __device__ __forceinline__ void cp_async8(double* dst, const double* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
 }
+// the same with compile-time byte offsets folded into the instruction ([reg + imm] on both sides): one LDGSTS and
+// nothing else per copy -- every extra instruction per copy is paid in full here (the kernels are issue bound)
+template <int SOFF, int GOFF>
+__device__ __forceinline__ void cp_async8_imm(uint32_t s, const double* g) {
+  asm volatile("cp.async.ca.shared.global [%0 + %2], [%1 + %3], 8;" :: "r"(s), "l"(g), "n"(SOFF), "n"(GOFF) : "memory");
+}
+// lanes copy doubles lane + 32 q, q = 0 .. ceil(N / 32) - 1, of a contiguous run of N doubles (N known at compile time)
+template <int N, int... Q>
+__device__ __forceinline__ void cp_async_run_full(uint32_t s, const double* g, int lane, std::integer_sequence<int, Q...>) {
+  // s and g already include the lane offset; only the last, partial, row of 32 needs a predicate
+  (((Q + 1) * 32 <= N ? cp_async8_imm<Q * 256, Q * 256>(s, g)
+                      : (lane + Q * 32 < N ? cp_async8_imm<Q * 256, Q * 256>(s, g) : (void)0)), ...);
+}
+template <int N>
+__device__ __forceinline__ void cp_async_run(double* dst, const double* src, int n, int lane) {
+  // n <= N valid doubles; n == N (every chunk but the last) takes the predicate-free form
+  const uint32_t s = smem_u32(dst + lane);
+  const double* g = src + lane;
+  if (n == N) {
+    cp_async_run_full<N>(s, g, lane, std::make_integer_sequence<int, (N + 31) / 32>{});
+  } else {
+    for (int k = lane; k < n; k += 32) cp_async8(dst + k, src + k);
+  }
+}
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
@@ -230,13 +254,42 @@ using DivLayout = DivLayoutT<3>;
 
 // ES (NX = 1 only): the geometric factors are laid out J(E, 3) -- "es,sij,ej->ei", reference
 // examples/dg_wave_div.py:14 -- instead of J(3, E); the slot then holds them as [el][s]
-template <int NX, bool ES = false>
+// plain (non-TMA) producer of one divergence chunk.  It lives in its own kernel instantiation (TMA = false): compiled
+// into the TMA kernels as a cold branch -- inline or as a call -- it cost them 2-5 % (A/B on one box, profiles/r02_ab_dmma.md)
+template <int NX, bool ES>
+__device__ __forceinline__ void div_issue_plain(double* s, uint64_t* bar, const double* __restrict__ Jg,
+                                             const double* __restrict__ ug, long long e0, long long E, int lane) {
+  using L = DivLayoutT<NX>;
+    // rows of elements past E are not copied: they hold stale (finite or not) data, are computed -- the rows of a
+    // DMMA tile are independent -- and never stored
+    // fully unrolled with immediate offsets: a rolled loop serialises on the address register of each LDGSTS
+    // (long-scoreboard release), ~57 round trips per chunk (profiles/r02_ncu_div_p4_odd.txt)
+    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+#pragma unroll
+    for (int x = 0; x < NX; ++x)
+      cp_async_run<L::U_SLAB>(s + x * L::U_SLAB, ug + ((long long)x * E + e0) * 35, ne * 35, lane);
+    if (ES) {
+#pragma unroll
+      for (int q = 0; q < (3 * kCH + 31) / 32; ++q)
+        if (lane + 32 * q < 3 * ne) cp_async8(s + NX * L::U_SLAB + lane + 32 * q, Jg + e0 * 3 + lane + 32 * q);
+    } else {
+      // k = lane + 32 q  <->  row xr = k / 16 = (lane >> 4) + 2 q, element el = lane & 15
+      const int el = lane & (kCH - 1);
+      const double* src = Jg + (long long)(lane >> 4) * E + e0 + el;
+#pragma unroll
+      for (int q = 0; q < (3 * NX * kCH + 31) / 32; ++q)
+        if (lane + 32 * q < 3 * NX * kCH && el < ne) cp_async8(s + NX * L::U_SLAB + lane + 32 * q, src + (long long)(2 * q) * E);
+    }
+    cp_async_arrive_noinc(bar);
+}
+
+template <int NX, bool ES = false, bool TMA = true>
 __device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps* maps,
                                           const double* __restrict__ Jg, const double* __restrict__ ug,
-                                          long long chunk, long long E, bool tma, int lane) {
+                                          long long chunk, long long E, int lane) {
   using L = DivLayoutT<NX>;
   const long long e0 = chunk * kCH;
-  if (tma) {
+  if constexpr (TMA) {
     if (elect_one()) {
       fence_proxy_async();
       mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
@@ -246,22 +299,7 @@ __device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps
       else    tma_load_2d(s + NX * L::U_SLAB, &maps->jac, (int)e0, 0, bar);      // J[3 NX][16 el]
     }
   } else {
-    // rows of elements past E are not copied: they hold stale (finite or not) data, are computed -- the rows of a
-    // DMMA tile are independent -- and never stored
-    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-    for (int x = 0; x < NX; ++x) {
-      const double* src = ug + ((long long)x * E + e0) * 35;
-      for (int k = lane; k < ne * 35; k += 32) cp_async8(s + x * L::U_SLAB + k, src + k);
-    }
-    for (int k = lane; k < 3 * NX * kCH; k += 32) {
-      if (ES) {
-        if (k < 3 * ne) cp_async8(s + NX * L::U_SLAB + k, Jg + e0 * 3 + k);
-      } else {
-        const int xr = k / kCH, el = k - xr * kCH;
-        if (el < ne) cp_async8(s + NX * L::U_SLAB + k, Jg + (long long)xr * E + e0 + el);
-      }
-    }
-    cp_async_arrive_noinc(bar);
+    div_issue_plain<NX, ES>(s, bar, Jg, ug, e0, E, lane);
   }
 }
 
@@ -271,7 +309,7 @@ __device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps
 // memory for two more warps (19 KB per warp staged -> 10 warps, 14.6 KB direct -> 12 warps)
 // DBG (profiling aid, results invalid): 1 = no conversion (A fragments = constants), 2 = no left-over
 // DFMAs, 4 = no epilogue
-template <int NW, bool STAGED, int DBG = 0, int NX = 3, bool ES = false>
+template <int NW, bool STAGED, int DBG = 0, int NX = 3, bool ES = false, bool TMA = true>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, const double* __restrict__ Dg,
            const double* __restrict__ ug, double* __restrict__ outg, long long E, int flags) {
@@ -287,7 +325,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
-    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], (flags & kFlagTma) ? 1 : 32);   // plain producer: every lane arrives
+    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], TMA ? 1 : 32);   // plain producer: every lane arrives
     *work_ctr = 0u;
     mbar_fence_init();
   }
@@ -301,9 +339,10 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   const WorkQueue wq{work_ctr, nchunks};
   const int g = lane >> 2, t = lane & 3, tpad = t < 3 ? t : 2;
 
-  const bool tma = flags & kFlagTma, dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
+  constexpr bool tma = TMA;
+  const bool dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
   long long cur = wq.take(lane), nxt = wq.take(lane);
-  if (cur < nchunks && !dbg_noload) div_issue<NX, ES>(s, bar, &maps, Jg, ug, cur, E, tma, lane);
+  if (cur < nchunks && !dbg_noload) div_issue<NX, ES, TMA>(s, bar, &maps, Jg, ug, cur, E, lane);
   // operator tables are staged while the first TMA loads are in flight
   // main operator fragments, column tiles in pairs so that one LDS.128 feeds two of them:
   // sB[((kt*2 + p)*32 + lane)*2 + h] = D[r][8(2p+h)+g][4jq+t]
@@ -354,7 +393,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
       }
     }
     __syncwarp();                                  // every lane is done reading the slot
-    if (nxt < nchunks && !dbg_noload) div_issue<NX, ES>(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
+    if (nxt < nchunks && !dbg_noload) div_issue<NX, ES, TMA>(s, bar, &maps, Jg, ug, nxt, E, lane);
     const unsigned tk = wq.ticket(lane);          // ticket after next; its latency hides under the DMMAs
 
     // ---- DMMA stream ----
@@ -499,26 +538,52 @@ struct GradLayout {
   static constexpr uint32_t SLOT_BYTES = SLOT_DOUBLES * 8;
 };
 
-__device__ __forceinline__ void grad_issue(double* s, uint64_t* bar, const OpMaps* maps,
-                                           const double* __restrict__ Jg, const double* __restrict__ ug,
-                                           long long chunk, long long E, bool tma, int lane) {
+__device__ __forceinline__ void grad_issue_plain(double* s, uint64_t* bar, const double* __restrict__ Jg,
+                                              const double* __restrict__ ug, long long e0, long long E, int lane) {
   using L = GradLayout;
-  const long long e0 = chunk * kCH;
-  if (tma) {
-    if (elect_one()) {
-      fence_proxy_async();
-      mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
-      tma_load_2d(s, &maps->in, 0, (int)(chunk * (kCH / 2)), bar);               // u[16 el][35]
-      tma_load_2d(s + L::U_SLAB, &maps->jac, (int)e0, 0, bar);                   // J[9][16 el]
-    }
-  } else {
     const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-    for (int k = lane; k < ne * 35; k += 32) cp_async8(s + k, ug + e0 * 35 + k);
-    for (int k = lane; k < 9 * kCH; k += 32) {
-      const int xr = k / kCH, el = k - xr * kCH;
-      if (el < ne) cp_async8(s + L::U_SLAB + k, Jg + (long long)xr * E + e0 + el);
+    cp_async_run<L::U_SLAB>(s, ug + e0 * 35, ne * 35, lane);
+    {
+      const int el = lane & (kCH - 1);
+      const double* src = Jg + (long long)(lane >> 4) * E + e0 + el;
+#pragma unroll
+      for (int q = 0; q < (9 * kCH + 31) / 32; ++q)
+        if (lane + 32 * q < 9 * kCH && el < ne) cp_async8(s + L::U_SLAB + lane + 32 * q, src + (long long)(2 * q) * E);
     }
     cp_async_arrive_noinc(bar);
+}
+
+// TMA instantiation: `tma_ok` = the launch flag kFlagTma.  With it clear the slot is filled synchronously (LDG -> STS ->
+// one arrival: round 1's plain path).  The library's launchers never clear it -- operands that do not qualify for
+// tensor maps go to the TMA = false instantiation (cp.async producer) -- but the branch stays: with it compiled out,
+// ptxas allocates / schedules the hot loop of the grad and lift kernels 1-3 % slower (A/B of both builds on one box,
+// profiles/r02_ab_dmma.md).  It costs nothing at run time (one uniform predicate per work item).
+template <bool TMA>
+__device__ __forceinline__ void grad_issue(double* s, uint64_t* bar, const OpMaps* maps,
+                                           const double* __restrict__ Jg, const double* __restrict__ ug,
+                                           long long chunk, long long E, bool tma_ok, int lane) {
+  using L = GradLayout;
+  const long long e0 = chunk * kCH;
+  if constexpr (TMA) {
+    if (tma_ok) {
+      if (elect_one()) {
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
+        tma_load_2d(s, &maps->in, 0, (int)(chunk * (kCH / 2)), bar);               // u[16 el][35]
+        tma_load_2d(s + L::U_SLAB, &maps->jac, (int)e0, 0, bar);                   // J[9][16 el]
+      }
+    } else {
+      const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+      for (int k = lane; k < L::U_SLAB; k += 32) s[k] = (k < ne * 35) ? ug[e0 * 35 + k] : 0.0;
+      for (int k = lane; k < 9 * kCH; k += 32) {
+        const int xr = k / kCH, el = k - xr * kCH;
+        s[L::U_SLAB + k] = (el < ne) ? Jg[(long long)xr * E + e0 + el] : 0.0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    }
+  } else {
+    grad_issue_plain(s, bar, Jg, ug, e0, E, lane);
   }
 }
 
@@ -566,7 +631,7 @@ __device__ __forceinline__ void grad_group(const double* __restrict__ sB, const 
   }
 }
 
-template <int NW>
+template <int NW, bool TMA = true>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, const double* __restrict__ Dg,
             const double* __restrict__ ug, double* __restrict__ outg, long long E, int flags) {
@@ -581,7 +646,7 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
-    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], (flags & kFlagTma) ? 1 : 32);   // plain producer: every lane arrives
+    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], TMA ? 1 : 32);   // plain producer: every lane arrives
     *work_ctr = 0u;
     mbar_fence_init();
   }
@@ -595,9 +660,10 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
   const WorkQueue wq{work_ctr, nchunks};
   const int g = lane >> 2, t = lane & 3, tpad = t < 3 ? t : 2;
 
-  const bool tma = flags & kFlagTma, dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
+  const bool tma = TMA && (flags & kFlagTma);
+  const bool dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
   long long cur = wq.take(lane), nxt = wq.take(lane);
-  if (cur < nchunks && !dbg_noload) grad_issue(s, bar, &maps, Jg, ug, cur, E, tma, lane);
+  if (cur < nchunks && !dbg_noload) grad_issue<TMA>(s, bar, &maps, Jg, ug, cur, E, tma, lane);
   // operator tables are staged while the first TMA loads are in flight
   // sB[(tile*KT + kt)*32 + lane]: B[k = t][n = c], c = lane>>2 -> value v = 2*tile + (c&1) of lane c>>1
   _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
@@ -623,7 +689,7 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
       for (int xr = 0; xr < 9; ++xr) Jr[m][xr] = sJ[xr * kCH + el];
     }
     __syncwarp();
-    if (nxt < nchunks && !dbg_noload) grad_issue(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
+    if (nxt < nchunks && !dbg_noload) grad_issue<TMA>(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
     const unsigned tk = wq.ticket(lane);
 
     const long long e0 = cur * kCH;
@@ -664,35 +730,58 @@ struct LiftLayout {
 };
 
 template <bool FE>
-__device__ __forceinline__ void lift_issue(double* s, uint64_t* bar, const CUtensorMap* map_v,
-                                           const CUtensorMap* map_j, const double* __restrict__ Jg,
-                                           const double* __restrict__ vg, long long chunk, long long E,
-                                           bool tma, int lane) {
+__device__ __forceinline__ void lift_issue_plain(double* s, uint64_t* bar, const double* __restrict__ Jg,
+                                              const double* __restrict__ vg, long long e0, long long E, int lane) {
   using L = LiftLayout;
-  const long long e0 = chunk * kCH;
-  if (tma) {
-    if (elect_one()) {
-      fence_proxy_async();
-      mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
-      tma_load_3d(s, map_v, 0, (int)(chunk * (kCH / 2)), 0, bar);                // v[4][16 el][15]
-      if (FE) tma_load_2d(s + 4 * L::V_SLAB, map_j, (int)e0, 0, bar);            // Jface[4][16 el]
-      else    tma_load_2d(s + 4 * L::V_SLAB, map_j, 0, (int)(chunk * (kCH / 2)), bar);   // J[16 el][4]
-    }
-  } else {
     const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-    for (int f = 0; f < 4; ++f) {
-      const double* src = vg + ((long long)f * E + e0) * 15;
-      for (int k = lane; k < ne * 15; k += 32) cp_async8(s + f * L::V_SLAB + k, src + k);
-    }
-    for (int k = lane; k < 4 * kCH; k += 32) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+      cp_async_run<L::V_SLAB>(s + f * L::V_SLAB, vg + ((long long)f * E + e0) * 15, ne * 15, lane);
+#pragma unroll
+    for (int q = 0; q < (4 * kCH) / 32; ++q) {
+      const int k = lane + 32 * q;
       if (FE) { const int f = k / kCH, el = k - f * kCH; if (el < ne) cp_async8(s + 4 * L::V_SLAB + k, Jg + (long long)f * E + e0 + el); }
       else    { const int el = k / 4; if (el < ne) cp_async8(s + 4 * L::V_SLAB + k, Jg + e0 * 4 + k); }
     }
     cp_async_arrive_noinc(bar);
+}
+
+template <bool FE, bool TMA>
+__device__ __forceinline__ void lift_issue(double* s, uint64_t* bar, const CUtensorMap* map_v,
+                                           const CUtensorMap* map_j, const double* __restrict__ Jg,
+                                           const double* __restrict__ vg, long long chunk, long long E,
+                                           bool tma_ok, int lane) {
+  using L = LiftLayout;
+  const long long e0 = chunk * kCH;
+  if constexpr (TMA) {
+    if (tma_ok) {
+      if (elect_one()) {
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
+        tma_load_3d(s, map_v, 0, (int)(chunk * (kCH / 2)), 0, bar);                // v[4][16 el][15]
+        if (FE) tma_load_2d(s + 4 * L::V_SLAB, map_j, (int)e0, 0, bar);            // Jface[4][16 el]
+        else    tma_load_2d(s + 4 * L::V_SLAB, map_j, 0, (int)(chunk * (kCH / 2)), bar);   // J[16 el][4]
+      }
+    } else {                                                                       // see grad_issue
+      const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+      for (int f = 0; f < 4; ++f)
+        for (int k = lane; k < L::V_SLAB; k += 32)
+          s[f * L::V_SLAB + k] = (k < ne * 15) ? vg[((long long)f * E + e0) * 15 + k] : 0.0;
+      for (int k = lane; k < 4 * kCH; k += 32) {
+        double v = 0.0;
+        if (FE) { const int f = k / kCH, el = k - f * kCH; if (el < ne) v = Jg[(long long)f * E + e0 + el]; }
+        else    { const int el = k / 4; if (el < ne) v = Jg[e0 * 4 + k]; }
+        s[4 * L::V_SLAB + k] = v;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    }
+  } else {
+    lift_issue_plain<FE>(s, bar, Jg, vg, e0, E, lane);
   }
 }
 
-template <int NW, bool FE>
+template <int NW, bool FE, bool TMA = true>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg,
             const double* __restrict__ Og, const __grid_constant__ OpmatRows rows, int nrows, long long E, int flags) {
@@ -708,7 +797,7 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
-    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], (flags & kFlagTma) ? 1 : 32);   // plain producer: every lane arrives
+    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], TMA ? 1 : 32);   // plain producer: every lane arrives
     *work_ctr = 0u;
     mbar_fence_init();
   }
@@ -723,11 +812,11 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
   const WorkQueue wq{work_ctr, nchunks};
   const int g = lane >> 2, t = lane & 3;
 
-  const bool tma = flags & kFlagTma;
+  const bool tma = TMA && (flags & kFlagTma);
   long long cur = wq.take(lane), nxt = wq.take(lane);
   int fld = 0;
   if (cur < nchunks)
-    lift_issue<FE>(s, bar, &maps.in[0], &maps.jac, Jg, static_cast<const double*>(rows.field[0]), cur, E, tma, lane);
+    lift_issue<FE, TMA>(s, bar, &maps.in[0], &maps.jac, Jg, static_cast<const double*>(rows.field[0]), cur, E, tma, lane);
   // operator tables are staged while the first TMA loads are in flight
   // sB[(kt*4 + nt)*32 + lane] = Op(f, 8nt+g, j),  k = 4kt+t = 15 f + j
   _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
@@ -780,7 +869,7 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
     const int nfld = advance ? 0 : fld + 1;
     const long long nchunk = advance ? nxt : cur;
     if (nchunk < nchunks)
-      lift_issue<FE>(s, bar, &maps.in[nfld], &maps.jac, Jg, static_cast<const double*>(rows.field[nfld]), nchunk, E, tma, lane);
+      lift_issue<FE, TMA>(s, bar, &maps.in[nfld], &maps.jac, Jg, static_cast<const double*>(rows.field[nfld]), nchunk, E, tma, lane);
     unsigned tk = 0;
     if (advance) tk = wq.ticket(lane);
 
@@ -982,6 +1071,56 @@ static void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned threads, 
   cudaLaunchKernelEx(&lc, kernel, std::forward<Args>(args)...);   // errors are picked up by post_launch()
 }
 
+// Operands that do not qualify for tensor maps (odd E, a base that is not 16-byte aligned): the TMA = false
+// instantiations, at the default warp counts (div 12 with direct stores, grad 10, lift 16).
+static int launch_dmma_plain(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows,
+                             long long E, int stagger, const DevInfo& di, cudaStream_t st) {
+  const long long nchunks = (E + kCH - 1) / kCH;
+  const double* J = static_cast<const double*>(jac);
+  const double* O = static_cast<const double*>(op);
+  auto grid_for = [&](int nw) {
+    const long long need = (nchunks + nw - 1) / nw;
+    return (unsigned)(di.sms < need ? di.sms : need);
+  };
+  const int flags = stagger << 8;
+  OpMaps maps{};
+  if (kind == FNSM_OP_DIV) {
+    constexpr int NW = 12;
+    const size_t smem = 8 * ((size_t)DivLayout::B_DOUBLES + (size_t)NW * DivLayout::SLOT_DOUBLES) + 8 * (size_t)NW + 8;
+    auto kernel = k_div_dmma<NW, false, 0, 3, false, false>;
+    if (int rc = set_smem(kernel, smem)) return rc;
+    for (int r = 0; r < nrows; ++r) {
+      launch_k(kernel, grid_for(NW), NW * 32, smem, st, maps, J, O, static_cast<const double*>(rows.field[r]),
+               static_cast<double*>(rows.out[r]), E, flags);
+      if (int rc = post_launch()) return rc;
+    }
+    return FNSM_OK;
+  }
+  if (kind == FNSM_OP_GRAD) {
+    constexpr int NW = 10;
+    const size_t smem = 8 * ((size_t)GradLayout::B_DOUBLES + (size_t)NW * (GradLayout::SLOT_DOUBLES + 3 * OUT_BLOCK)) + 8 * (size_t)NW + 8;
+    auto kernel = k_grad_dmma<NW, false>;
+    if (int rc = set_smem(kernel, smem)) return rc;
+    for (int r = 0; r < nrows; ++r) {
+      launch_k(kernel, grid_for(NW), NW * 32, smem, st, maps, J, O, static_cast<const double*>(rows.field[r]),
+               static_cast<double*>(rows.out[r]), E, flags);
+      if (int rc = post_launch()) return rc;
+    }
+    return FNSM_OK;
+  }
+  constexpr int NW = 16;
+  const size_t smem = 8 * ((size_t)LiftLayout::B_DOUBLES + (size_t)NW * (LiftLayout::SLOT_DOUBLES + OUT_BLOCK)) + 8 * (size_t)NW + 8;
+  LiftMaps lmaps{};
+  if (kind == FNSM_OP_LIFT_FE) {
+    if (int rc = set_smem(k_lift_dmma<NW, true, false>, smem)) return rc;
+    launch_k(k_lift_dmma<NW, true, false>, grid_for(NW), NW * 32, smem, st, lmaps, J, O, rows, nrows, E, flags);
+  } else {
+    if (int rc = set_smem(k_lift_dmma<NW, false, false>, smem)) return rc;
+    launch_k(k_lift_dmma<NW, false, false>, grid_for(NW), NW * 32, smem, st, lmaps, J, O, rows, nrows, E, flags);
+  }
+  return post_launch();
+}
+
 template <int NW>
 static int launch_dmma_nw(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows,
                           long long E, const fnsm_cfg* cfg, const DevInfo& di, cudaStream_t st) {
@@ -998,6 +1137,7 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
   if (stagger == 0) stagger = kDefaultStagger;
   if (stagger < 0) stagger = 0;                       // negative: off
   if (stagger > (1 << 20)) stagger = 1 << 20;
+  if (!tma) return launch_dmma_plain(kind, jac, op, rows, nrows, E, stagger, di, st);
   auto grid_for_items = [&](long long nitems) {
     long long grid = di.sms;                          // one persistent CTA per SM
     const long long need = (nitems + NW - 1) / NW;      // no more CTAs than can be kept busy
@@ -1024,7 +1164,13 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
       bool ok = tma && map_erows(&maps.jac, J, E, 9);
       if (is_div) ok = ok && map_slabs(&maps.in, u, E, 35, 3) && map_rows(&maps.out, out, E, 35);
       else        ok = ok && map_rows(&maps.in, u, E, 35) && map_slabs(&maps.out, out, E, 35, 3);
-      const int flags = (ok ? kFlagTma : 0) | (dbg & (kFlagNoLoad | kFlagNoStore)) | (stagger << 8);
+      if (!ok) {                                        // the driver refused a descriptor: plain producer for this row
+        OpmatRows one{};
+        one.field[0] = u; one.out[0] = out;
+        if (int rc = launch_dmma_plain(kind, jac, op, one, 1, E, stagger, di, st)) return rc;
+        continue;
+      }
+      const int flags = kFlagTma | (dbg & (kFlagNoLoad | kFlagNoStore)) | (stagger << 8);
       if (is_div) {
         const int dbgk = cfg ? cfg->reserved[2] : 0;
         if (staged && NW == 10 && dbgk) {
@@ -1054,7 +1200,8 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
   bool ok = tma && (kind == FNSM_OP_LIFT_FE ? map_erows(&maps.jac, J, E, 4) : map_rows(&maps.jac, J, E, 4));
   for (int r = 0; r < nrows && ok; ++r)
     ok = map_slabs(&maps.in[r], rows.field[r], E, 15, 4) && map_rows(&maps.out[r], rows.out[r], E, 35);
-  const int flags = (ok ? kFlagTma : 0) | (stagger << 8);
+  if (!ok) return launch_dmma_plain(kind, jac, op, rows, nrows, E, stagger, di, st);
+  const int flags = kFlagTma | (stagger << 8);
   if (kind == FNSM_OP_LIFT_FE) {
     if (int rc = set_smem(k_lift_dmma<NW, true>, smem)) return rc;
     launch_k(k_lift_dmma<NW, true>, grid, threads, smem, st, maps, J, O, rows, nrows, E, flags);

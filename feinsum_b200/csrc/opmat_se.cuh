@@ -206,8 +206,10 @@ static int launch_se_p4(const void* op, const SeRows& rows, int nrows, long long
   using L = DivLayoutT<1>;
   const size_t smem = 8 * ((size_t)L::B_DOUBLES + (size_t)NW * L::SLOT_DOUBLES) + 8 * (size_t)NW + 8;
   if (smem > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
-  auto kernel = k_div_dmma<NW, false, 0, 1, ES>;
+  auto kernel = k_div_dmma<NW, false, 0, 1, ES, true>;
+  auto kernel_plain = k_div_dmma<NW, false, 0, 1, ES, false>;
   if (int rc = set_smem(kernel, smem)) return rc;
+  if (int rc = set_smem(kernel_plain, smem)) return rc;
   const long long nchunks = (E + kCH - 1) / kCH;
   const long long need = (nchunks + NW - 1) / NW;
   const unsigned grid = (unsigned)(di.sms < need ? di.sms : need);
@@ -216,12 +218,12 @@ static int launch_se_p4(const void* op, const SeRows& rows, int nrows, long long
     const double* J = static_cast<const double*>(rows.jac[r]);
     const double* u = static_cast<const double*>(rows.field[r]);
     double* out = static_cast<double*>(rows.out[r]);
-    OpMaps maps;
+    OpMaps maps{};
     const bool tma = !force_plain && E % 2 == 0 && E < (1LL << 31) - kCH && aligned16(J) && aligned16(u) && aligned16(out) &&
                      (ES ? map_rows(&maps.jac, J, E, 3) : map_erows(&maps.jac, J, E, 3)) &&
                      map_rows(&maps.in, u, E, 35) && map_rows(&maps.out, out, E, 35);
-    launch_k(kernel, grid, NW * 32, smem, st, maps, J, static_cast<const double*>(op), u, out, (long long)E,
-             tma ? kFlagTma : 0);
+    launch_k(tma ? kernel : kernel_plain, grid, NW * 32, smem, st, maps, J, static_cast<const double*>(op), u, out,
+             (long long)E, tma ? kFlagTma : 0);
     if (int rc = post_launch()) return rc;
   }
   return FNSM_OK;

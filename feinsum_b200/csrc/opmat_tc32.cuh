@@ -525,7 +525,6 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
     if (fld == 0) {
 #pragma unroll
       for (int f = 0; f < 4; ++f) Jf[f] = Jn[f];
-      load_j(tile + tstride, Jn);
     }
     mbar_wait(&full[s], (uint32_t)(it >> 1) & 1u);
     // ---- row of the slot -> A_hi / A_lo in TMEM ----
@@ -567,6 +566,7 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
     }
     if (it + 2 < nitems) issue(it + 2, s);
     if (TMA && leader) tma_store_wait_read();            // the stage is free again (previous item's store)
+    if (fld == 0) load_j(tile + tstride, Jn);            // next tile's face Jacobians, behind the last use of Jf (see k_div_tc32)
     mbar_wait(mma_done, (uint32_t)it & 1u);
     tc_fence_after();
     group_barrier(bar_id, L::GT);                          // ... and every thread knows it (plain: all drained it)
@@ -728,11 +728,6 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
     float Jr[9];
 #pragma unroll
     for (int xr = 0; xr < 9; ++xr) Jr[xr] = Jn[xr];
-    {
-      const long long tn = tile + tstride, e = tn * L::TM + row;
-#pragma unroll
-      for (int xr = 0; xr < 9; ++xr) Jn[xr] = (tn < ntiles && e < E) ? __ldg(Jg + (long long)xr * E + e) : 0.f;
-    }
     mbar_wait(full, it & 1u);
 #pragma unroll
     for (int r = 0; r < L::NCHUNK; ++r) {
@@ -776,6 +771,14 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
         if (tile + tstride < ntiles) fetch(tile + tstride);
         if (TMA && leader) tma_store_wait_read();        // the stage is free again (previous tile's store)
       }
+    }
+    {
+      // Jacobian of the next tile: issued only now, behind the last use of Jr.  (Issued at the top of the iteration,
+      // the loads shared a scoreboard with the ones that produced Jr, and the first FMUL of the fold waited for them:
+      // 12 % of the kernel's stall samples, profiles/r02_ncu_div_p4_f32_odd.txt.)  They land under the MMA wait.
+      const long long tn = tile + tstride, e = tn * L::TM + row;
+#pragma unroll
+      for (int xr = 0; xr < 9; ++xr) Jn[xr] = (tn < ntiles && e < E) ? __ldg(Jg + (long long)xr * E + e) : 0.f;
     }
     mbar_wait(&mma_done[1], it & 1u);
     mbar_wait(&mma_done[2], it & 1u);
