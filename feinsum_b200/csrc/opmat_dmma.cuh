@@ -130,6 +130,9 @@ __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 lanes
 __device__ __forceinline__ void cp_async8(double* dst, const double* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async8_rr(uint32_t dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
+}
 // the same with compile-time byte offsets folded into the instruction ([reg + imm] on both sides): one LDGSTS and
 // nothing else per copy -- every extra instruction per copy is paid in full here (the kernels are issue bound)
 template <int SOFF, int GOFF>
@@ -157,6 +160,13 @@ __device__ __forceinline__ void cp_async_run(double* dst, const double* src, int
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
+
+// f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N - 1>{}): a loop whose index is a constant
+// expression inside the body (usable as an asm immediate)
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) { (f(std::integral_constant<int, I>{}), ...); }
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
 
 // lets a kernel launched with programmatic stream serialization behind this one start as SMs free up (launch_k)
 __device__ __forceinline__ void release_dependent_kernels() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -283,6 +293,46 @@ __device__ __forceinline__ void div_issue_plain(double* s, uint64_t* bar, const 
     cp_async_arrive_noinc(bar);
 }
 
+// The plain producer SPREAD over the DMMA stream.  Issued as one burst (div_issue_plain), the ~60 LDGSTS of a chunk
+// pile up in the MIO queue in front of the other warps' B-fragment LDS and their DMMA streams stall on the short
+// scoreboard (17.6 % of the stall samples against 5.7 % with TMA, profiles/r02_ncu_div_p4_odd.txt).  Two copies
+// behind every k-tile's eight DMMAs keep the queue shallow; the slot was consumed into registers before the stream
+// starts, so it can be refilled piecemeal.
+template <int NX>
+struct DivPlainCtx {
+  uint32_t s;                 // shared address of the slot + lane * 8
+  const double* u[NX];        // global address of slab x of the next chunk + lane
+  const double* j;            // J: address of row (lane >> 4), element e0 + (lane & 15)  [ES: e0 * 3 + lane]
+  long long E2;               // 2 E: stride between the rows two apart
+  int nvalid, ne, lane;       // valid doubles per slab, valid elements
+  bool active;
+};
+template <int NX, bool ES, int KTI>
+__device__ __forceinline__ void div_plain_step(const DivPlainCtx<NX>& c) {
+  using L = DivLayoutT<NX>;
+  constexpr int ROWS = (L::U_SLAB + 31) / 32;                 // 18 rows of 32 doubles per slab
+  constexpr int NU = NX * ROWS, PER = (NU + L::KT - 1) / L::KT;
+  if (!c.active) return;
+  constexpr int C0 = KTI * PER, C1 = C0 + 1;
+  if constexpr (C0 < NU) {
+    constexpr int x = C0 / ROWS, q = C0 % ROWS;
+    if (c.lane + 32 * q < c.nvalid) cp_async8_imm<(x * L::U_SLAB + 32 * q) * 8, 32 * q * 8>(c.s, c.u[x]);
+  }
+  if constexpr (PER > 1 && C1 < NU) {
+    constexpr int x = C1 / ROWS, q = C1 % ROWS;
+    if (c.lane + 32 * q < c.nvalid) cp_async8_imm<(x * L::U_SLAB + 32 * q) * 8, 32 * q * 8>(c.s, c.u[x]);
+  }
+  // the Jacobian rows ride on the first few k-tiles
+  constexpr int NJQ = (3 * NX * kCH + 31) / 32;
+  if constexpr (KTI < NJQ) {
+    if (ES) {
+      if (c.lane + 32 * KTI < 3 * c.ne) cp_async8_imm<(NX * L::U_SLAB + 32 * KTI) * 8, 32 * KTI * 8>(c.s, c.j);
+    } else if (c.lane + 32 * KTI < 3 * NX * kCH && (c.lane & (kCH - 1)) < c.ne) {
+      cp_async8_imm<(NX * L::U_SLAB + 32 * KTI) * 8, 0>(c.s, c.j + (long long)KTI * c.E2);
+    }
+  }
+}
+
 template <int NX, bool ES = false, bool TMA = true>
 __device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps* maps,
                                           const double* __restrict__ Jg, const double* __restrict__ ug,
@@ -393,7 +443,21 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
       }
     }
     __syncwarp();                                  // every lane is done reading the slot
-    if (nxt < nchunks && !dbg_noload) div_issue<NX, ES, TMA>(s, bar, &maps, Jg, ug, nxt, E, lane);
+    DivPlainCtx<NX> pc;
+    if constexpr (TMA) {
+      if (nxt < nchunks && !dbg_noload) div_issue<NX, ES, TMA>(s, bar, &maps, Jg, ug, nxt, E, lane);
+    } else {                                       // plain producer: spread over the DMMA stream below
+      const long long e0n = nxt * kCH;
+      pc.active = nxt < nchunks;
+      pc.ne = (int)((E - e0n < kCH) ? (E - e0n) : kCH);
+      pc.nvalid = pc.ne * 35;
+      pc.lane = lane;
+      pc.s = smem_u32(s + lane);
+      pc.E2 = 2 * E;
+#pragma unroll
+      for (int x = 0; x < NX; ++x) pc.u[x] = ug + ((long long)x * E + e0n) * 35 + lane;
+      pc.j = ES ? Jg + e0n * 3 + lane : Jg + (long long)(lane >> 4) * E + e0n + (lane & (kCH - 1));
+    }
     const unsigned tk = wq.ticket(lane);          // ticket after next; its latency hides under the DMMAs
 
     // ---- DMMA stream ----
@@ -405,7 +469,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
     // B fragments are fetched one k-tile ahead of their DMMAs (ptxas otherwise funnels every fragment
     // through one register pair and exposes the LDS latency to each pair of DMMAs)
     const uint32_t bB = smem_u32(sB) + lane * 16, bL = smem_u32(sL) + t * 32;
-    {
+    if constexpr (TMA) {
       double2 bq[2][2];
       bq[0][0] = lds_v2(bB); bq[0][1] = lds_v2(bB + 512);
 #pragma unroll
@@ -420,6 +484,23 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
           dmma884(acc[m][3], a[m][kt], bq[c][1].y);
         }
       }
+    } else {
+      // the same stream with the next chunk's copies woven in (compile-time k-tile index: immediate offsets)
+      double2 bq[2][2];
+      bq[0][0] = lds_v2(bB); bq[0][1] = lds_v2(bB + 512);
+      static_for<L::KT>([&](auto ktc) {
+        constexpr int kt = decltype(ktc)::value, c = kt & 1, nx = c ^ 1;
+        if (kt + 1 < L::KT) { bq[nx][0] = lds_v2(bB + (kt + 1) * 1024); bq[nx][1] = lds_v2(bB + (kt + 1) * 1024 + 512); }
+#pragma unroll
+        for (int m = 0; m < kME; ++m) {
+          dmma884(acc[m][0], a[m][kt], bq[c][0].x);
+          dmma884(acc[m][1], a[m][kt], bq[c][0].y);
+          dmma884(acc[m][2], a[m][kt], bq[c][1].x);
+          dmma884(acc[m][3], a[m][kt], bq[c][1].y);
+        }
+        div_plain_step<NX, ES, kt>(pc);
+      });
+      if (pc.active) cp_async_arrive_noinc(bar);
     }
     const long long e0 = cur * kCH;
     // ---- dofs 0..31 leave the registers first ... ----
@@ -558,6 +639,31 @@ __device__ __forceinline__ void grad_issue_plain(double* s, uint64_t* bar, const
 // tensor maps go to the TMA = false instantiation (cp.async producer) -- but the branch stays: with it compiled out,
 // ptxas allocates / schedules the hot loop of the grad and lift kernels 1-3 % slower (A/B of both builds on one box,
 // profiles/r02_ab_dmma.md).  It costs nothing at run time (one uniform predicate per work item).
+// plain producer of a grad chunk in five bursts, one behind each group of column tiles: 18 rows of 32 doubles of u
+// (four per burst) + 5 of J (one per burst)
+struct GradPlainCtx {
+  uint32_t s;
+  const double* u;            // next chunk + lane
+  const double* j;            // row (lane >> 4), element e0 + (lane & 15)
+  long long E2;
+  int nvalid, ne, lane;
+  bool active;
+};
+template <int G>
+__device__ __forceinline__ void grad_plain_step(const GradPlainCtx& c) {
+  using L = GradLayout;
+  constexpr int ROWS = (L::U_SLAB + 31) / 32;                   // 18
+  if (!c.active) return;
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    constexpr int q0 = 4 * G;
+    const int q = q0 + h;
+    if (q < ROWS && c.lane + 32 * q < c.nvalid) cp_async8_rr(c.s + 32 * q * 8, c.u + 32 * q);
+  }
+  if (c.lane + 32 * G < 9 * kCH && (c.lane & (kCH - 1)) < c.ne)
+    cp_async8_rr(c.s + (L::U_SLAB + 32 * G) * 8, c.j + (long long)G * c.E2);
+}
+
 template <bool TMA>
 __device__ __forceinline__ void grad_issue(double* s, uint64_t* bar, const OpMaps* maps,
                                            const double* __restrict__ Jg, const double* __restrict__ ug,
@@ -689,15 +795,33 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
       for (int xr = 0; xr < 9; ++xr) Jr[m][xr] = sJ[xr * kCH + el];
     }
     __syncwarp();
-    if (nxt < nchunks && !dbg_noload) grad_issue<TMA>(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
+    GradPlainCtx pc;
+    if constexpr (TMA) {
+      if (nxt < nchunks && !dbg_noload) grad_issue<TMA>(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
+    } else {
+      const long long e0n = nxt * kCH;
+      pc.active = nxt < nchunks;
+      pc.ne = (int)((E - e0n < kCH) ? (E - e0n) : kCH);
+      pc.nvalid = pc.ne * 35;
+      pc.lane = lane;
+      pc.s = smem_u32(s + lane);
+      pc.E2 = 2 * E;
+      pc.u = ug + e0n * 35 + lane;
+      pc.j = Jg + (long long)(lane >> 4) * E + e0n + (lane & (kCH - 1));
+    }
     const unsigned tk = wq.ticket(lane);
 
     const long long e0 = cur * kCH;
     grad_group<0, 3>(sB, a, Jr, stage, g, t, lane);
+    if constexpr (!TMA) grad_plain_step<0>(pc);
     grad_group<3, 3>(sB, a, Jr, stage, g, t, lane);
+    if constexpr (!TMA) grad_plain_step<1>(pc);
     grad_group<6, 3>(sB, a, Jr, stage, g, t, lane);
+    if constexpr (!TMA) grad_plain_step<2>(pc);
     grad_group<9, 3>(sB, a, Jr, stage, g, t, lane);
+    if constexpr (!TMA) grad_plain_step<3>(pc);
     grad_group<12, 2>(sB, a, Jr, stage, g, t, lane);
+    if constexpr (!TMA) { grad_plain_step<4>(pc); if (pc.active) cp_async_arrive_noinc(bar); }
     fence_proxy_async();
     __syncwarp();
     if (!dbg_nostore) {
@@ -744,6 +868,39 @@ __device__ __forceinline__ void lift_issue_plain(double* s, uint64_t* bar, const
       else    { const int el = k / 4; if (el < ne) cp_async8(s + 4 * L::V_SLAB + k, Jg + e0 * 4 + k); }
     }
     cp_async_arrive_noinc(bar);
+}
+
+// plain producer of a lift item spread over its 15 k-tiles (see DivPlainCtx): 8 rows of 32 doubles per face slab
+// (the last one half full) = 32 copies + 2 for the face Jacobians
+struct LiftPlainCtx {
+  uint32_t s;
+  const double* v[4];         // face slab f of the next item + lane
+  const double* j;            // FE: row (lane >> 4), element e0 + (lane & 15); EF: e0 * 4 + lane
+  long long E2;
+  int nvalid, ne, lane;
+  bool active;
+};
+template <bool FE, int KTI>
+__device__ __forceinline__ void lift_plain_step(const LiftPlainCtx& c) {
+  using L = LiftLayout;
+  constexpr int ROWS = (L::V_SLAB + 31) / 32, NV = 4 * ROWS;    // 8, 32
+  constexpr int PER = (NV + L::KT - 1) / L::KT;                 // 3 (k-tiles 0..10 carry the slabs)
+  if (!c.active) return;
+#pragma unroll
+  for (int h = 0; h < PER; ++h) {
+    const int ci = KTI * PER + h;                               // constant after unrolling
+    if (ci < NV) {
+      const int f = ci / ROWS, q = ci % ROWS;
+      if (c.lane + 32 * q < c.nvalid)
+        cp_async8_rr(c.s + (f * L::V_SLAB + 32 * q) * 8, c.v[f] + 32 * q);
+    }
+  }
+  if constexpr (KTI >= L::KT - 2) {                             // Jacobians on the last two k-tiles
+    constexpr int q = KTI - (L::KT - 2);
+    const int k = c.lane + 32 * q;
+    if (FE) { if ((c.lane & (kCH - 1)) < c.ne) cp_async8_rr(c.s + (4 * L::V_SLAB + 32 * q) * 8, c.j + (long long)q * c.E2); }
+    else    { if ((k >> 2) < c.ne) cp_async8_rr(c.s + (4 * L::V_SLAB + 32 * q) * 8, c.j + 32 * q); }
+  }
 }
 
 template <bool FE, bool TMA>
@@ -868,8 +1025,23 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
     const bool advance = fld + 1 == nrows;
     const int nfld = advance ? 0 : fld + 1;
     const long long nchunk = advance ? nxt : cur;
-    if (nchunk < nchunks)
-      lift_issue<FE, TMA>(s, bar, &maps.in[nfld], &maps.jac, Jg, static_cast<const double*>(rows.field[nfld]), nchunk, E, tma, lane);
+    LiftPlainCtx pc;
+    if constexpr (TMA) {
+      if (nchunk < nchunks)
+        lift_issue<FE, TMA>(s, bar, &maps.in[nfld], &maps.jac, Jg, static_cast<const double*>(rows.field[nfld]), nchunk, E, tma, lane);
+    } else {                                       // plain producer: spread over the k-tiles below
+      const long long e0n = nchunk * kCH;
+      const double* vg = static_cast<const double*>(rows.field[nfld]);
+      pc.active = nchunk < nchunks;
+      pc.ne = (int)((E - e0n < kCH) ? (E - e0n) : kCH);
+      pc.nvalid = pc.ne * 15;
+      pc.lane = lane;
+      pc.s = smem_u32(s + lane);
+      pc.E2 = 2 * E;
+#pragma unroll
+      for (int f = 0; f < 4; ++f) pc.v[f] = vg + ((long long)f * E + e0n) * 15 + lane;
+      pc.j = FE ? Jg + (long long)(lane >> 4) * E + e0n + (lane & (kCH - 1)) : Jg + e0n * 4 + lane;
+    }
     unsigned tk = 0;
     if (advance) tk = wq.ticket(lane);
 
@@ -882,23 +1054,47 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
 #pragma unroll
       for (int d = 0; d < kNL; ++d) { accL[0][m][d] = 0.0; accL[1][m][d] = 0.0; }
     }
+    if constexpr (TMA) {
 #pragma unroll
-    for (int kt = 0; kt < L::KT; ++kt) {
-      const double* bp = sB + (kt * kNT) * 32 + lane;
+      for (int kt = 0; kt < L::KT; ++kt) {
+        const double* bp = sB + (kt * kNT) * 32 + lane;
 #pragma unroll
-      for (int nt = 0; nt < kNT; ++nt) {
-        const double b = bp[nt * 32];
+        for (int nt = 0; nt < kNT; ++nt) {
+          const double b = bp[nt * 32];
 #pragma unroll
-        for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m][kt], b);
+          for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m][kt], b);
+        }
+        const double2 l01 = *reinterpret_cast<const double2*>(sL + (kt * 4 + t) * 4);
+        const double l2 = sL[(kt * 4 + t) * 4 + 2];
+#pragma unroll
+        for (int m = 0; m < kME; ++m) {
+          accL[kt & 1][m][0] = fma(a[m][kt], l01.x, accL[kt & 1][m][0]);
+          accL[kt & 1][m][1] = fma(a[m][kt], l01.y, accL[kt & 1][m][1]);
+          accL[kt & 1][m][2] = fma(a[m][kt], l2, accL[kt & 1][m][2]);
+        }
       }
-      const double2 l01 = *reinterpret_cast<const double2*>(sL + (kt * 4 + t) * 4);
-      const double l2 = sL[(kt * 4 + t) * 4 + 2];
-#pragma unroll
-      for (int m = 0; m < kME; ++m) {
-        accL[kt & 1][m][0] = fma(a[m][kt], l01.x, accL[kt & 1][m][0]);
-        accL[kt & 1][m][1] = fma(a[m][kt], l01.y, accL[kt & 1][m][1]);
-        accL[kt & 1][m][2] = fma(a[m][kt], l2, accL[kt & 1][m][2]);
-      }
+    } else {
+      auto ktile = [&](auto ktc) {
+        constexpr int kt = decltype(ktc)::value;
+        const double* bp = sB + (kt * kNT) * 32 + lane;
+  #pragma unroll
+        for (int nt = 0; nt < kNT; ++nt) {
+          const double b = bp[nt * 32];
+  #pragma unroll
+          for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m][kt], b);
+        }
+        const double2 l01 = *reinterpret_cast<const double2*>(sL + (kt * 4 + t) * 4);
+        const double l2 = sL[(kt * 4 + t) * 4 + 2];
+  #pragma unroll
+        for (int m = 0; m < kME; ++m) {
+          accL[kt & 1][m][0] = fma(a[m][kt], l01.x, accL[kt & 1][m][0]);
+          accL[kt & 1][m][1] = fma(a[m][kt], l01.y, accL[kt & 1][m][1]);
+          accL[kt & 1][m][2] = fma(a[m][kt], l2, accL[kt & 1][m][2]);
+        }
+        lift_plain_step<FE, kt>(pc);
+      };
+      static_for<L::KT>(ktile);
+      if (pc.active) cp_async_arrive_noinc(bar);
     }
 
     const long long c = cur;
