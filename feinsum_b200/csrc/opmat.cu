@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "opmat_simt.cuh"
 #include "opmat_dmma.cuh"
+#include "opmat_grad2.cuh"
 #include "opmat_tf32.cuh"
 #include "opmat_tc32.cuh"
 #include "opmat_dmma_gen.cuh"
@@ -33,7 +34,7 @@ int opmat_cfg_space(int kernel_id, fnsm_cfg_range* out, int cap) {
   set_range(&tmp[n++], "tile_e", 8, 64, 8, 16);        // simt: elements per CTA tile
   set_range(&tmp[n++], "ctas_per_sm", 1, 8, 1, 0);     // persistent grid size
   set_range(&tmp[n++], "threads", 128, 512, 32, 0);   // dmma: 32 * warps per persistent CTA (4, 8..12, 14, 16)
-  set_range(&tmp[n++], "stages", 0, 1, 1, 1);          // dmma: shared-memory slots per warp
+  set_range(&tmp[n++], "stages", 0, 2, 1, 1);          // dmma: shared-memory slots per warp; 2 = grad2 formulation (fp64 grad p = 4)
   for (int i = 0; i < n && i < cap; ++i) out[i] = tmp[i];
   return n;
 }
@@ -111,7 +112,17 @@ static int opmat_dispatch(int kind, int dtype, const void* jac, const void* op,
       if (!rows.field[r] || !rows.out[r]) return FNSM_E_BAD_ARG;
     }
     int rc;
-    if (variant == 1 && dtype == FNSM_F64)
+    if (variant == 1 && dtype == FNSM_F64 && tensor_ok && kind == FNSM_OP_GRAD && cfg && cfg->stages == 2) {
+      // grad2 (opmat_grad2.cuh): divergence tables + direct stores; selected with stages = 2 while it is being measured
+      const int th = cfg->threads ? cfg->threads : 384;
+      const bool fp = cfg->reserved[0] & 1;
+      const double* Jd = static_cast<const double*>(jac);
+      const double* Dd = static_cast<const double*>(op);
+      rc = th == 384 ? launch_grad2<12>(Jd, Dd, rows, nr, E, fp, di, st)
+         : th == 320 ? launch_grad2<10>(Jd, Dd, rows, nr, E, fp, di, st)
+         : th == 512 ? launch_grad2<16>(Jd, Dd, rows, nr, E, fp, di, st)
+         : th == 448 ? launch_grad2<14>(Jd, Dd, rows, nr, E, fp, di, st) : (int)FNSM_E_BAD_CONFIG;
+    } else if (variant == 1 && dtype == FNSM_F64)
       rc = tensor_ok ? launch_dmma(kind, jac, op, rows, nr, n_outer, ni, nj, E, cfg, di, st)
                      : launch_dmma_gen(kind, jac, op, rows, nr, ni, E, cfg, di, st);
     else if (variant == 3)

@@ -1413,7 +1413,7 @@ static int launch_dmma(int kind, const void* jac, const void* op, const OpmatRow
                        const DevInfo& di, cudaStream_t st) {
   (void)n_outer; (void)ni; (void)nj;
   if (cfg && cfg->ctas_per_sm > 1) return FNSM_E_BAD_CONFIG;
-  if (cfg && (cfg->stages < 0 || cfg->stages > 1)) return FNSM_E_BAD_CONFIG;
+  if (cfg && (cfg->stages < 0 || cfg->stages > 2)) return FNSM_E_BAD_CONFIG;
   // defaults from the round-1 sweeps on B200 (profiles/): grad 10 warps, div 12 (direct stores), lift 16
   // (lift fits 16 warps in shared memory and, at 126 registers, in the register file: 79.6 % -> 81.1 %)
   const int dflt = kind == FNSM_OP_GRAD ? 320 : (kind == FNSM_OP_DIV ? 384 : 512);

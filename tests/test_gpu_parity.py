@@ -441,3 +441,14 @@ def test_shared_operator_family_es_layout(cq, shape, n):
     plan = generate_cuda(e).plan
     assert plan.kernel_id == "opmat_se" and plan.facts["es"] == 1
     check(e, n, cq)
+
+
+@pytest.mark.parametrize("threads", [0, 320, 384])
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 100, 1001, 10007, 10008, 100000])
+def test_grad_fp64_second_formulation(cq, n, threads):
+    """grad2 (csrc/opmat_grad2.cuh): the divergence kernel's operator tables, (r, nt) column tiles, J applied in
+    registers, direct stores -- TMA producer for even n, woven cp.async producer for odd n."""
+    params = {"variant": 1, "stages": 2}
+    if threads:
+        params["threads"] = threads
+    check(E.grad(), n, cq, **params)
