@@ -119,7 +119,7 @@ def test_autotune_searches_records_and_short_circuits(tmp_path, fake_clock):
     with pytest.raises(ValueError):
         f.autotune(E.div(), "relative/path.py", cq, db_path=db)
     best = f.autotune(E.div(), mod, cq, db_path=db, long_dim_length=1000)
-    assert best == {"warps": 10, "variant": 1}
+    assert best == {"warps": 10, "variant": 1, "ctas_per_sm": 0, "tile_e8": 0}   # p = 4: grid / tile knobs are fixed
     assert len(fake_clock) == 5                                   # warps 8..12 timed, 13..16 illegal
     assert len(f.query(E.div(), cq.device, database=db)) == 5     # illegal points are not recorded
     fake_clock.clear()
@@ -180,3 +180,24 @@ def test_shipped_database_has_b200_facts():
     renamed = f.einsum("abn,nq,bpq->anp", f.array("Jac", (3, 3, "N")), f.array("v", ("N", 35)), f.array("Dmat", (3, 35, 35)))
     assert len(f.query(renamed, dev)) == len(f.query(E.grad(), dev))
     assert len(f.get_timed_einsums_in_db(dev)) == 10
+
+
+def test_launch_spaces_depend_on_the_shape():
+    """the lower orders tune over the grid and the tile, p = 4 over the warp count (and, for the
+    fp64 gradient, the formulation)."""
+    from feinsum_b200.tuning import get_transform_func_from_module_path
+
+    pt = get_transform_func_from_module_path(os.path.join(IMPLS, "xre_rij_ej_to_xei.py"))
+    p4 = pt.parameter_space(f.canonicalize_einsum(E.grad()))
+    p2 = pt.parameter_space(f.canonicalize_einsum(E.grad(ndof=10)))
+    p4f = pt.parameter_space(E.grad(dtype="float32"))
+    assert p4["warps"] == list(range(8, 17)) and p4["ctas_per_sm"] == [0] and p4["tile_e8"] == [0]
+    assert p4["formulation"] == [1, 2] and p4f["formulation"] == [1] and p4f["variant"] == [1, 2, 3]
+    assert p2["warps"] == [8] and p2["ctas_per_sm"] == [0, 1, 2, 3, 4] and p2["formulation"] == [1]
+    prog = pt.bind_args(E.grad(), warps=12, formulation=2)(f.generate_cuda(E.grad()))
+    assert dict(prog.params) == {"threads": 384, "variant": 1, "stages": 2}
+    lo = get_transform_func_from_module_path(os.path.join(IMPLS, "ifj_fe_fej_to_ei.py"))
+    e = E.lift_fe(nvol=10, nfd=6)
+    assert lo.parameter_space(e)["ctas_per_sm"] == [0, 1, 2, 3, 4]
+    assert dict(lo.bind_args(e, warps=8, ctas_per_sm=2)(f.generate_cuda(e)).params) == \
+        {"threads": 256, "variant": 1, "ctas_per_sm": 2}
