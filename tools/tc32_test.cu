@@ -34,7 +34,7 @@ static int test_lift(bool fe, long long E, int reps, const fnsm::DevInfo& di) {
   fnsm::OpmatRows rows{};
   for (int k = 0; k < nf; ++k) { rows.field[k] = dv + (size_t)k * 4 * E * 15; rows.out[k] = dout + (size_t)k * E * 35; }
   const int kind = fe ? FNSM_OP_LIFT_FE : FNSM_OP_LIFT_EF;
-  int rc = fnsm::launch_lift_tc32<35, 15>(kind, dJ, dO, rows, nf, E, di, 0);
+  int rc = fnsm::launch_lift_tc32<35, 15>(kind, dJ, dO, rows, nf, E, di, 0, false);
   printf("launch rc=%d\n", rc);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
@@ -60,9 +60,9 @@ static int test_lift(bool fe, long long E, int reps, const fnsm::DevInfo& di) {
   printf("lift_%s E=%lld checked=%lld bad=%lld worst_rel=%.3e\n", fe ? "fe" : "ef", E, checked, bad, worst);
   if (reps > 0) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    for (int k = 0; k < 3; ++k) fnsm::launch_lift_tc32<35, 15>(kind, dJ, dO, rows, nf, E, di, 0);
+    for (int k = 0; k < 3; ++k) fnsm::launch_lift_tc32<35, 15>(kind, dJ, dO, rows, nf, E, di, 0, false);
     cudaEventRecord(a);
-    for (int k = 0; k < reps; ++k) fnsm::launch_lift_tc32<35, 15>(kind, dJ, dO, rows, nf, E, di, 0);
+    for (int k = 0; k < reps; ++k) fnsm::launch_lift_tc32<35, 15>(kind, dJ, dO, rows, nf, E, di, 0, false);
     cudaEventRecord(b); CK(cudaEventSynchronize(b));
     float ms; cudaEventElapsedTime(&ms, a, b); ms /= reps;
     printf("lift_tc32 E=%lld: %.4f ms  %.1f GB/s  %.1f TFLOP/s(17040/elt)\n", E, ms, 1536.0 * E / ms * 1e-6, 17040.0 * E / ms * 1e-9);
@@ -84,7 +84,7 @@ static int test_div(long long E, int reps, const fnsm::DevInfo& di) {
   CK(cudaMemcpy(dD, D.data(), D.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(du, u.data(), u.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dout, 0xff, out.size() * 4));
-  int rc = fnsm::launch_div_tc32<35>(dJ, dD, du, dout, E, di, 0);
+  int rc = fnsm::launch_div_tc32<35>(dJ, dD, du, dout, E, di, 0, false);
   printf("launch rc=%d\n", rc);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
@@ -108,9 +108,9 @@ static int test_div(long long E, int reps, const fnsm::DevInfo& di) {
   printf("div E=%lld checked=%lld bad=%lld worst_rel=%.3e\n", E, checked, bad, worst);
   if (reps > 0) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    for (int k = 0; k < 3; ++k) fnsm::launch_div_tc32<35>(dJ, dD, du, dout, E, di, 0);
+    for (int k = 0; k < 3; ++k) fnsm::launch_div_tc32<35>(dJ, dD, du, dout, E, di, 0, false);
     cudaEventRecord(a);
-    for (int k = 0; k < reps; ++k) fnsm::launch_div_tc32<35>(dJ, dD, du, dout, E, di, 0);
+    for (int k = 0; k < reps; ++k) fnsm::launch_div_tc32<35>(dJ, dD, du, dout, E, di, 0, false);
     cudaEventRecord(b); CK(cudaEventSynchronize(b));
     float ms; cudaEventElapsedTime(&ms, a, b); ms /= reps;
     printf("div_tc32 E=%lld: %.4f ms  %.1f GB/s  %.1f TFLOP/s(7980/elt)\n", E, ms, 596.0 * E / ms * 1e-6, 7980.0 * E / ms * 1e-9);
@@ -139,7 +139,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dD, D.data(), D.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(du, u.data(), u.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dout, 0xff, out.size() * 4));
-  int rc = fnsm::launch_grad_tc32<35>(dJ, dD, du, dout, E, di, 0);
+  int rc = fnsm::launch_grad_tc32<35>(dJ, dD, du, dout, E, di, 0, false);
   printf("launch rc=%d\n", rc);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
@@ -162,9 +162,9 @@ int main(int argc, char** argv) {
   printf("E=%lld checked=%lld bad=%lld worst_rel=%.3e\n", E, checked, bad, worst);
   if (reps > 0) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    for (int k = 0; k < 3; ++k) fnsm::launch_grad_tc32<35>(dJ, dD, du, dout, E, di, 0);
+    for (int k = 0; k < 3; ++k) fnsm::launch_grad_tc32<35>(dJ, dD, du, dout, E, di, 0, false);
     cudaEventRecord(a);
-    for (int k = 0; k < reps; ++k) fnsm::launch_grad_tc32<35>(dJ, dD, du, dout, E, di, 0);
+    for (int k = 0; k < reps; ++k) fnsm::launch_grad_tc32<35>(dJ, dD, du, dout, E, di, 0, false);
     cudaEventRecord(b); CK(cudaEventSynchronize(b));
     float ms; cudaEventElapsedTime(&ms, a, b); ms /= reps;
     printf("grad_tc32 E=%lld: %.4f ms  %.1f GB/s  %.1f TFLOP/s(7980/elt)\n", E, ms, 596.0 * E / ms * 1e-6, 7980.0 * E / ms * 1e-9);
