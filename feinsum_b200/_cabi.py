@@ -152,7 +152,10 @@ def make_cfg(params: dict[str, Any] | None) -> Any:
             cfg.reserved[0] = int(val)
             continue
         if key == "dbgk":  # dmma div: compile-time profiling variants (results invalid)
-            cfg.reserved[2] = int(val)
+            cfg.reserved[2] = (cfg.reserved[2] & ~15) | (int(val) & 15)
+            continue
+        if key == "fast_start":  # dmma kernels: 1 / 2 force the small-launch instantiations on / off (0: by size)
+            cfg.reserved[2] = (cfg.reserved[2] & 15) | ((int(val) & 3) << 4)
             continue
         if key == "stagger":  # dmma kernels: start-up phase offset (cycles) between warps of one sub-partition
             cfg.reserved[1] = int(val)

@@ -42,6 +42,27 @@
 
 namespace fnsm {
 
+// Phase stamps for tools/timeline.cu (compiled out of the library): globaltimer at a few points of every warp's life,
+// so that the fixed cost of a launch (prologue, operator staging, first load, tail) can be read off at small E.
+#ifdef FNSM_TIMELINE
+constexpr int kTlLaunches = 16, kTlSlots = 12;
+__device__ unsigned long long fnsm_tl[kTlLaunches][160][16][kTlSlots];
+__device__ unsigned fnsm_tl_ctr;
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define FNSM_TL_DECL __shared__ unsigned tl_launch_; \
+  if (threadIdx.x == 0) tl_launch_ = (atomicAdd(&fnsm_tl_ctr, 1u) / gridDim.x) % kTlLaunches;
+#define FNSM_TL(slot) do { if ((threadIdx.x & 31) == 0) fnsm_tl[tl_launch_][blockIdx.x][threadIdx.x >> 5][slot] = tl_now(); } while (0)
+#define FNSM_TL_VAL(slot, v) do { if ((threadIdx.x & 31) == 0) fnsm_tl[tl_launch_][blockIdx.x][threadIdx.x >> 5][slot] = (v); } while (0)
+#else
+#define FNSM_TL_DECL
+#define FNSM_TL(slot) do { } while (0)
+#define FNSM_TL_VAL(slot, v) do { } while (0)
+#endif
+
 // ----------------------------------------------------------------- PTX -----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -157,6 +178,38 @@ __device__ __forceinline__ void cp_async_run(double* dst, const double* src, int
     for (int k = lane; k < n; k += 32) cp_async8(dst + k, src + k);
   }
 }
+__device__ __forceinline__ void cp_async16(double* dst, const double* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// Operator staging, first half: the raw operator (N doubles, row-major as the caller holds it) is copied into a
+// scratch region of shared memory with coalesced cp.async -- every copy of the CTA in flight at once -- and the
+// kernels then permute it into DMMA fragment order from shared memory.  Round 1 gathered the fragment order straight
+// from global memory: 13 dependent-latency loads per thread on 8 sectors each, with all 148 CTAs hammering the same
+// 29 KB of L2 -- 4.6 us of every launch (tools/timeline, profiles/r02_small_e.md), a fifth of the run time at
+// E = 100 000.  The copies go out ahead of the first work-item loads (they gate everything); the caller then waits
+// (stage_operator_raw_wait) and synchronises the CTA.
+template <int N, int THREADS>
+__device__ __forceinline__ void stage_operator_raw(double* scratch, const double* __restrict__ g) {
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    constexpr int N16 = N / 2;
+#pragma unroll
+    for (int q = 0; q < (N16 + THREADS - 1) / THREADS; ++q) {
+      const int k = (int)threadIdx.x + q * THREADS;
+      if (k < N16) cp_async16(scratch + 2 * k, g + 2 * k);
+    }
+    if ((N & 1) && threadIdx.x == 0) cp_async8(scratch + N - 1, g + N - 1);
+  } else {
+#pragma unroll
+    for (int q = 0; q < (N + THREADS - 1) / THREADS; ++q) {
+      const int k = (int)threadIdx.x + q * THREADS;
+      if (k < N) cp_async8(scratch + k, g + k);
+    }
+  }
+  // its own group: the wait below must not cover the work-item copies of the plain producers, which are issued
+  // behind it and complete on their slot's mbarrier
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_operator_raw_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
@@ -226,6 +279,10 @@ struct LiftMaps { CUtensorMap jac; CUtensorMap in[8]; CUtensorMap out[8]; };
 constexpr int kFlagTma = 1;        // operands qualify for the TMA path
 constexpr int kFlagNoLoad = 2;     // profiling aid: skip loads  (results invalid)
 constexpr int kFlagNoStore = 4;    // profiling aid: skip stores (results invalid)
+// The kernel is independent of the grid ahead of it on the stream (wave_3d_p4: the three einsums touch disjoint
+// buffers): it loads right away and executes griddepcontrol.wait only before it exits.  Without the flag the wait
+// comes before the first global access, so only the launch latency and the on-chip set-up overlap the previous tail.
+constexpr int kFlagIndependent = 8;
 constexpr int kDefaultStagger = 0; // cycles; bits 8.. of `flags` carry the start-up phase offset
 
 // CTA-local dynamic work distribution: CTA b owns the items b, b + G, b + 2G, ...; its warps draw
@@ -359,12 +416,21 @@ __device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps
 // memory for two more warps (19 KB per warp staged -> 10 warps, 14.6 KB direct -> 12 warps)
 // DBG (profiling aid, results invalid): 1 = no conversion (A fragments = constants), 2 = no left-over
 // DFMAs, 4 = no epilogue
-template <int NW, bool STAGED, int DBG = 0, int NX = 3, bool ES = false, bool TMA = true>
+// FS ("fast start", the instantiation small launches take): griddepcontrol.wait before the first global access (the
+// launch then carries the programmatic-serialization attribute and its set-up hides behind the previous kernel's
+// tail) and the operator staged through shared memory (stage_operator_raw).  Worth 4-5 us per launch; the hot loop
+// ptxas builds around it is 1-2 % slower (register allocation), so larger launches (fast_start())
+// keep the FS = false code, which is the round-1 kernel token for token.
+template <int NW, bool STAGED, int DBG = 0, int NX = 3, bool ES = false, bool TMA = true, bool FS = false>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, const double* __restrict__ Dg,
            const double* __restrict__ ug, double* __restrict__ outg, long long E, int flags) {
   using L = DivLayoutT<NX>;
   release_dependent_kernels();
+  FNSM_TL_DECL
+#ifdef FNSM_TIMELINE
+  const unsigned long long tl_entry_ = tl_now();
+#endif
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sB = reinterpret_cast<double*>(smem_raw);
   double* sL = sB + L::B_MAIN;
@@ -380,6 +446,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
     mbar_fence_init();
   }
   __syncthreads();
+  FNSM_TL_VAL(0, tl_entry_);
 
   double* s = slots + (size_t)warp * L::SLOT_DOUBLES;
   double* stage = stages + (size_t)warp * (STAGED ? OUT_BLOCK : 0);
@@ -391,29 +458,76 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
 
   constexpr bool tma = TMA;
   const bool dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
-  long long cur = wq.take(lane), nxt = wq.take(lane);
-  if (cur < nchunks && !dbg_noload) div_issue<NX, ES, TMA>(s, bar, &maps, Jg, ug, cur, E, lane);
+  if constexpr (FS) { if (!(flags & kFlagIndependent)) wait_for_previous_kernels(); }   // nothing global has been read yet
+  FNSM_TL(1);
+  // FS: tickets are drawn ONE item ahead (at the start of the iteration that needs them) instead of two.  With ~4
+  // items per warp a depth of two fixes most of the assignment at launch, and a warp of a slower sub-partition ends
+  // up with the last item while others idle (last warps 8-10 us behind the first, tools/timeline).
+  long long cur = wq.take(lane), nxt = FS ? 0 : wq.take(lane);
+  // The raw operator is staged through the slots of the last NSCR warps (there is no other free shared memory);
+  // those warps issue their first loads once the tables are in fragment order.
+  constexpr int RAW = 3 * 35 * 35;
+  constexpr int NSCR = (RAW + L::SLOT_DOUBLES - 1) / L::SLOT_DOUBLES;
+  constexpr bool kRawStage = FS && NSCR <= NW;
+  static_assert(!FS || kRawStage, "fast start needs NSCR slots of scratch");
+  const bool late = kRawStage && warp >= NW - NSCR;
+  if constexpr (kRawStage) stage_operator_raw<RAW, NW * 32>(slots + (size_t)(NW - NSCR) * L::SLOT_DOUBLES, Dg);
+  if (cur < nchunks && !dbg_noload && !late) div_issue<NX, ES, TMA>(s, bar, &maps, Jg, ug, cur, E, lane);
   // operator tables are staged while the first TMA loads are in flight
   // main operator fragments, column tiles in pairs so that one LDS.128 feeds two of them:
   // sB[((kt*2 + p)*32 + lane)*2 + h] = D[r][8(2p+h)+g][4jq+t]
-  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
-  for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
-    const int h = idx & 1, ln = (idx >> 1) & 31, p = (idx >> 6) & 1, kt = idx >> 7;
-    const int g = ln >> 2, t = ln & 3, jq = kt / 3, r = kt - 3 * jq;
-    const int i = 8 * (2 * p + h) + g, j = 4 * jq + t;
-    sB[idx] = (j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
-  }
   // left-over dofs: sL[(kt*4 + t)*4 + d] = D[r][32+d][4jq+t]
-  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
-  for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
-    const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
-    const int jq = kt / 3, r = kt - 3 * jq, j = 4 * jq + t;
-    sL[idx] = (d < kNL && j < 35) ? Dg[(r * 35 + 32 + d) * 35 + j] : 0.0;
+  if constexpr (kRawStage) {
+    const double* raw = slots + (size_t)(NW - NSCR) * L::SLOT_DOUBLES;
+    stage_operator_raw_wait();
+    FNSM_TL(8);
+    __syncthreads();
+    FNSM_TL(9);
+    // 128 table entries per k-tile and a CTA of a multiple of 128 threads: (h, lane, p) are fixed per thread and
+    // only the k-tile moves, kt = kt0 + (NW / 4) q -- hardly any index arithmetic per entry (the generic loop
+    // spent 1.5 us here, tools/timeline)
+    static_assert(!FS || (NW % 4 == 0 && L::B_MAIN % (NW * 32) == 0), "table permutation assumes whole k-tiles per pass");
+    {
+      const int idx0 = (int)threadIdx.x & 127, kt0 = (int)threadIdx.x >> 7;
+      const int h = idx0 & 1, ln = (idx0 >> 1) & 31, p = idx0 >> 6;
+      const int gg = ln >> 2, tt = ln & 3;
+      const double* src = raw + (8 * (2 * p + h) + gg) * 35 + tt;
+#pragma unroll
+      for (int q = 0; q < L::B_MAIN / (NW * 32); ++q) {
+        const int kt = kt0 + (NW / 4) * q, jq = kt / 3, r = kt - 3 * jq;
+        sB[kt * 128 + idx0] = (4 * jq + tt < 35) ? src[r * 1225 + 4 * jq] : 0.0;
+      }
+    }
+    for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
+      const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
+      const int jq = kt / 3, r = kt - 3 * jq, j = 4 * jq + t;
+      sL[idx] = (d < kNL && j < 35) ? raw[(r * 35 + 32 + d) * 35 + j] : 0.0;
+    }
+    __syncthreads();
+    if (cur < nchunks && !dbg_noload && late) div_issue<NX, ES, TMA>(s, bar, &maps, Jg, ug, cur, E, lane);
+  } else {
+    _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
+    for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
+      const int h = idx & 1, ln = (idx >> 1) & 31, p = (idx >> 6) & 1, kt = idx >> 7;
+      const int g = ln >> 2, t = ln & 3, jq = kt / 3, r = kt - 3 * jq;
+      const int i = 8 * (2 * p + h) + g, j = 4 * jq + t;
+      sB[idx] = (j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
+    }
+    _Pragma("unroll 4")
+    for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
+      const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
+      const int jq = kt / 3, r = kt - 3 * jq, j = 4 * jq + t;
+      sL[idx] = (d < kNL && j < 35) ? Dg[(r * 35 + 32 + d) * 35 + j] : 0.0;
+    }
+    __syncthreads();
   }
-  __syncthreads();
+  FNSM_TL(2);
   stagger_start(warp, flags >> 8);
   for (uint32_t n = 0; cur < nchunks; ++n) {
     if (!dbg_noload) mbar_wait(bar, n & 1u);
+    unsigned tk = 0;
+    if (FS) tk = wq.ticket(lane);                 // resolved behind the conversion
+    if (n == 0) FNSM_TL(3);
     // ---- slot -> A fragments (Jacobian folded in) ----
     double a[kME][L::KT];
 #pragma unroll
@@ -443,6 +557,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
       }
     }
     __syncwarp();                                  // every lane is done reading the slot
+    if (FS) nxt = wq.resolve(tk);
     DivPlainCtx<NX> pc;
     if constexpr (TMA) {
       if (nxt < nchunks && !dbg_noload) div_issue<NX, ES, TMA>(s, bar, &maps, Jg, ug, nxt, E, lane);
@@ -458,7 +573,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
       for (int x = 0; x < NX; ++x) pc.u[x] = ug + ((long long)x * E + e0n) * 35 + lane;
       pc.j = ES ? Jg + e0n * 3 + lane : Jg + (long long)(lane >> 4) * E + e0n + (lane & (kCH - 1));
     }
-    const unsigned tk = wq.ticket(lane);          // ticket after next; its latency hides under the DMMAs
+    if (!FS) tk = wq.ticket(lane);                // ticket after next; its latency hides under the DMMAs
 
     // ---- DMMA stream ----
     double acc[kME][kNT][2];
@@ -596,11 +711,15 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
         }
       }
     }
+    if (n == 0) FNSM_TL(4);
+    FNSM_TL_VAL(7, n + 1);
     cur = nxt;
-    nxt = wq.resolve(tk);
+    if (!FS) nxt = wq.resolve(tk);
   }
+  FNSM_TL(5);
   if (lane == 0) tma_store_wait_all();
-  wait_for_previous_kernels();
+  FNSM_TL(6);
+  wait_for_previous_kernels();   // kFlagIndependent: the only wait; otherwise a no-op (the grid ahead has completed)
 }
 
 // ================================================================ GRAD =====
@@ -737,12 +856,16 @@ __device__ __forceinline__ void grad_group(const double* __restrict__ sB, const 
   }
 }
 
-template <int NW, bool TMA = true>
+template <int NW, bool TMA = true, bool FS = false>      // FS: see k_div_dmma
 __global__ void __launch_bounds__(NW * 32, 1)
 k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, const double* __restrict__ Dg,
             const double* __restrict__ ug, double* __restrict__ outg, long long E, int flags) {
   using L = GradLayout;
   release_dependent_kernels();
+  FNSM_TL_DECL
+#ifdef FNSM_TIMELINE
+  const unsigned long long tl_entry_ = tl_now();
+#endif
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sB = reinterpret_cast<double*>(smem_raw);
   double* slots = sB + L::B_DOUBLES;
@@ -757,6 +880,7 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
     mbar_fence_init();
   }
   __syncthreads();
+  FNSM_TL_VAL(0, tl_entry_);
 
   double* s = slots + (size_t)warp * L::SLOT_DOUBLES;
   double* stage = stages + (size_t)warp * 3 * OUT_BLOCK;      // [x][16][35]
@@ -768,21 +892,55 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
 
   const bool tma = TMA && (flags & kFlagTma);
   const bool dbg_noload = flags & kFlagNoLoad, dbg_nostore = flags & kFlagNoStore;
-  long long cur = wq.take(lane), nxt = wq.take(lane);
+  if constexpr (FS) { if (!(flags & kFlagIndependent)) wait_for_previous_kernels(); }   // nothing global has been read yet
+  FNSM_TL(1);
+  long long cur = wq.take(lane), nxt = FS ? 0 : wq.take(lane);     // FS: tickets one item ahead, see k_div_dmma
+  // fast start: raw D goes into the (still unused) output stages, ahead of the first work-item loads
+  static_assert((size_t)NW * 3 * OUT_BLOCK >= 3 * 35 * 35, "raw operator does not fit the stage area");
+  if constexpr (FS) stage_operator_raw<3 * 35 * 35, NW * 32>(stages, Dg);
   if (cur < nchunks && !dbg_noload) grad_issue<TMA>(s, bar, &maps, Jg, ug, cur, E, tma, lane);
-  // operator tables are staged while the first TMA loads are in flight
-  // sB[(tile*KT + kt)*32 + lane]: B[k = t][n = c], c = lane>>2 -> value v = 2*tile + (c&1) of lane c>>1
-  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
-  for (int idx = threadIdx.x; idx < L::B_DOUBLES; idx += blockDim.x) {
-    const int ln = idx & 31, kt = (idx >> 5) % L::KT, tile = (idx >> 5) / L::KT;
-    const int c = ln >> 2, t = ln & 3;
-    const int v = 2 * tile + (c & 1), i = 9 * (c >> 1) + v / 3, r = v % 3, j = 4 * kt + t;
-    sB[idx] = (v < 27 && i < 35 && j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
+  if constexpr (FS) {
+    // sB[(tile*KT + kt)*32 + lane]: B[k = t][n = c], c = lane>>2 -> value v = 2*tile + (c&1) of lane c>>1
+    stage_operator_raw_wait();
+    FNSM_TL(8);
+    __syncthreads();
+    FNSM_TL(9);
+    // a warp permutes units of (column tile, three k-tiles): the (dof, r) decode is done once per unit
+    const int c = lane >> 2, tt = lane & 3;
+#pragma unroll
+    for (int q = 0; q < (L::NTILE * 3 + NW - 1) / NW; ++q) {
+      const int u = warp + NW * q;
+      if (u < L::NTILE * 3) {
+        const int tile = u / 3, ktb = 3 * (u - 3 * tile);
+        const int v = 2 * tile + (c & 1), dv = v / 3, i = 9 * (c >> 1) + dv, r = v - 3 * dv;
+        const bool ok = v < 27 && i < 35;
+        const double* src = stages + (r * 35 + i) * 35 + tt;
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+          const int kt = ktb + kk;
+          sB[(tile * L::KT + kt) * 32 + lane] = (ok && 4 * kt + tt < 35) ? src[4 * kt] : 0.0;
+        }
+      }
+    }
+  } else {
+    // operator tables are staged while the first TMA loads are in flight
+    // sB[(tile*KT + kt)*32 + lane]: B[k = t][n = c], c = lane>>2 -> value v = 2*tile + (c&1) of lane c>>1
+    _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
+    for (int idx = threadIdx.x; idx < L::B_DOUBLES; idx += blockDim.x) {
+      const int ln = idx & 31, kt = (idx >> 5) % L::KT, tile = (idx >> 5) / L::KT;
+      const int c = ln >> 2, t = ln & 3;
+      const int v = 2 * tile + (c & 1), i = 9 * (c >> 1) + v / 3, r = v % 3, j = 4 * kt + t;
+      sB[idx] = (v < 27 && i < 35 && j < 35) ? Dg[(r * 35 + i) * 35 + j] : 0.0;
+    }
   }
   __syncthreads();
+  FNSM_TL(2);
   stagger_start(warp, flags >> 8);
   for (uint32_t n = 0; cur < nchunks; ++n) {
     if (!dbg_noload) mbar_wait(bar, n & 1u);
+    unsigned tk = 0;
+    if (FS) tk = wq.ticket(lane);
+    if (n == 0) FNSM_TL(3);
     double a[kME][L::KT];
     double Jr[kME][9];
 #pragma unroll
@@ -795,6 +953,7 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
       for (int xr = 0; xr < 9; ++xr) Jr[m][xr] = sJ[xr * kCH + el];
     }
     __syncwarp();
+    if (FS) nxt = wq.resolve(tk);
     GradPlainCtx pc;
     if constexpr (TMA) {
       if (nxt < nchunks && !dbg_noload) grad_issue<TMA>(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
@@ -809,7 +968,7 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
       pc.u = ug + e0n * 35 + lane;
       pc.j = Jg + (long long)(lane >> 4) * E + e0n + (lane & (kCH - 1));
     }
-    const unsigned tk = wq.ticket(lane);
+    if (!FS) tk = wq.ticket(lane);
 
     const long long e0 = cur * kCH;
     grad_group<0, 3>(sB, a, Jr, stage, g, t, lane);
@@ -833,11 +992,15 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
           flush_plain(outg + ((long long)x * E + e0) * 35, stage + x * OUT_BLOCK, e0, E, lane);
       }
     }
+    if (n == 0) FNSM_TL(4);
+    FNSM_TL_VAL(7, n + 1);
     cur = nxt;
-    nxt = wq.resolve(tk);
+    if (!FS) nxt = wq.resolve(tk);
   }
+  FNSM_TL(5);
   if (lane == 0) tma_store_wait_all();
-  wait_for_previous_kernels();
+  FNSM_TL(6);
+  wait_for_previous_kernels();   // kFlagIndependent: the only wait; otherwise a no-op (the grid ahead has completed)
 }
 
 // ================================================================ LIFT =====
@@ -938,12 +1101,19 @@ __device__ __forceinline__ void lift_issue(double* s, uint64_t* bar, const CUten
   }
 }
 
-template <int NW, bool FE, bool TMA = true>
+// FS ("fast start", see k_div_dmma) also switches the queue from whole chunks to single items (chunk, field): at
+// E = 100 000 a chunk-granular queue leaves 2.6 units per warp -- a 3 : 2 spread between warps and a 10 us tail
+// (tools/timeline); large launches keep the coarse queue, whose loop carries less state.
+template <int NW, bool FE, bool TMA = true, bool FS = false>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg,
             const double* __restrict__ Og, const __grid_constant__ OpmatRows rows, int nrows, long long E, int flags) {
   using L = LiftLayout;
   release_dependent_kernels();
+  FNSM_TL_DECL
+#ifdef FNSM_TIMELINE
+  const unsigned long long tl_entry_ = tl_now();
+#endif
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sB = reinterpret_cast<double*>(smem_raw);
   double* sL = sB + L::B_MAIN;
@@ -959,42 +1129,86 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
     mbar_fence_init();
   }
   __syncthreads();
+  FNSM_TL_VAL(0, tl_entry_);
 
   double* s = slots + (size_t)warp * L::SLOT_DOUBLES;
   double* stage = stages + (size_t)warp * OUT_BLOCK;
   uint64_t* bar = &bars[warp];
   const double* sJ = s + 4 * L::V_SLAB;
   const long long nchunks = (E + kCH - 1) / kCH;
-  // work unit of the queue = one chunk; the warp then walks the chunk's fields (items)
-  const WorkQueue wq{work_ctr, nchunks};
+  // work unit of the queue: a chunk (the warp walks its fields), or with FS one item, id = chunk * nrows + field
+  // (< 2^30: division by nrows <= 8 as a multiplication by ceil(2^32 / nrows), exact in that range)
+  const WorkQueue wq{work_ctr, FS ? nchunks * nrows : nchunks};
+  // (nrows = 1: the multiplier 2^32 does not fit, the quotient is the id itself)
+  const unsigned magic = nrows > 1 ? (unsigned)((0x100000000ull + (unsigned)nrows - 1) / (unsigned)nrows) : 0u;
   const int g = lane >> 2, t = lane & 3;
 
   const bool tma = TMA && (flags & kFlagTma);
-  long long cur = wq.take(lane), nxt = wq.take(lane);
+  if constexpr (FS) { if (!(flags & kFlagIndependent)) wait_for_previous_kernels(); }   // nothing global has been read yet
+  FNSM_TL(1);
+  // loop state: chunk and field of the current item, queue position after it
+  long long cur = wq.take(lane), nxt = FS ? 0 : wq.take(lane);     // FS: tickets one item ahead, see k_div_dmma
   int fld = 0;
-  if (cur < nchunks)
-    lift_issue<FE, TMA>(s, bar, &maps.in[0], &maps.jac, Jg, static_cast<const double*>(rows.field[0]), cur, E, tma, lane);
-  // operator tables are staged while the first TMA loads are in flight
-  // sB[(kt*4 + nt)*32 + lane] = Op(f, 8nt+g, j),  k = 4kt+t = 15 f + j
-  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
-  for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
-    const int ln = idx & 31, nt = (idx >> 5) % kNT, kt = (idx >> 5) / kNT;
-    const int g = ln >> 2, t = ln & 3, k = 4 * kt + t, f = k / 15, j = k - 15 * f;
-    const int i = 8 * nt + g;
-    sB[idx] = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
+  if (FS) {
+    const unsigned q = nrows > 1 ? __umulhi((unsigned)cur, magic) : (unsigned)cur;
+    fld = (int)((unsigned)cur - q * (unsigned)nrows);
+    cur = q;
   }
-  _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
-  for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
-    const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
-    const int k = 4 * kt + t, f = k / 15, j = k - 15 * f, i = 32 + d;
-    double v = 0.0;
-    if (d < kNL) v = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
-    sL[idx] = v;
+  // fast start: the raw operator goes into the (still unused) output stages, ahead of the first work-item loads
+  static_assert((size_t)NW * OUT_BLOCK >= 35 * 4 * 15, "raw operator does not fit the stage area");
+  if constexpr (FS) stage_operator_raw<35 * 4 * 15, NW * 32>(stages, Og);
+  if (cur < nchunks)
+    lift_issue<FE, TMA>(s, bar, &maps.in[fld], &maps.jac, Jg, static_cast<const double*>(rows.field[fld]), cur, E, tma, lane);
+  if constexpr (FS) {
+    // sB[(kt*4 + nt)*32 + lane] = Op(f, 8nt+g, j),  k = 4kt+t = 15 f + j
+    stage_operator_raw_wait();
+    FNSM_TL(8);
+    __syncthreads();
+    FNSM_TL(9);
+#pragma unroll
+    for (int q = 0; q < (L::B_MAIN + NW * 32 - 1) / (NW * 32); ++q) {
+      const int idx = (int)threadIdx.x + q * NW * 32;
+      if (idx < L::B_MAIN) {
+        const int ln = idx & 31, nt = (idx >> 5) % kNT, kt = (idx >> 5) / kNT;
+        const int g = ln >> 2, t = ln & 3, k = 4 * kt + t, f = k / 15, j = k - 15 * f;
+        const int i = 8 * nt + g;
+        sB[idx] = FE ? stages[(i * 4 + f) * 15 + j] : stages[(f * 35 + i) * 15 + j];
+      }
+    }
+    for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
+      const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
+      const int k = 4 * kt + t, f = k / 15, j = k - 15 * f, i = 32 + d;
+      double v = 0.0;
+      if (d < kNL) v = FE ? stages[(i * 4 + f) * 15 + j] : stages[(f * 35 + i) * 15 + j];
+      sL[idx] = v;
+    }
+  } else {
+    // operator tables are staged while the first TMA loads are in flight
+    // sB[(kt*4 + nt)*32 + lane] = Op(f, 8nt+g, j),  k = 4kt+t = 15 f + j
+    _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
+    for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
+      const int ln = idx & 31, nt = (idx >> 5) % kNT, kt = (idx >> 5) / kNT;
+      const int g = ln >> 2, t = ln & 3, k = 4 * kt + t, f = k / 15, j = k - 15 * f;
+      const int i = 8 * nt + g;
+      sB[idx] = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
+    }
+    _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
+    for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
+      const int d = idx & 3, t = (idx >> 2) & 3, kt = idx >> 4;
+      const int k = 4 * kt + t, f = k / 15, j = k - 15 * f, i = 32 + d;
+      double v = 0.0;
+      if (d < kNL) v = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
+      sL[idx] = v;
+    }
   }
   __syncthreads();
+  FNSM_TL(2);
   stagger_start(warp, flags >> 8);
   for (uint32_t n = 0; cur < nchunks; ++n) {
     mbar_wait(bar, n & 1u);
+    unsigned tk = 0;
+    if (FS) tk = wq.ticket(lane);
+    if (n == 0) FNSM_TL(3);
     double a[kME][L::KT];
 #pragma unroll
     for (int m = 0; m < kME; ++m) {
@@ -1021,10 +1235,21 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
       }
     }
     __syncwarp();
-    // next item: next field of this chunk, else field 0 of the next chunk
-    const bool advance = fld + 1 == nrows;
-    const int nfld = advance ? 0 : fld + 1;
-    const long long nchunk = advance ? nxt : cur;
+    if (FS) nxt = wq.resolve(tk);
+    // next item: (FS) the next queue position, else the next field of this chunk / field 0 of the next chunk
+    bool advance;
+    int nfld;
+    long long nchunk;
+    if (FS) {
+      advance = true;
+      const unsigned q = nrows > 1 ? __umulhi((unsigned)nxt, magic) : (unsigned)nxt;
+      nfld = (int)((unsigned)nxt - q * (unsigned)nrows);
+      nchunk = q;
+    } else {
+      advance = fld + 1 == nrows;
+      nfld = advance ? 0 : fld + 1;
+      nchunk = advance ? nxt : cur;
+    }
     LiftPlainCtx pc;
     if constexpr (TMA) {
       if (nchunk < nchunks)
@@ -1042,8 +1267,8 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
       for (int f = 0; f < 4; ++f) pc.v[f] = vg + ((long long)f * E + e0n) * 15 + lane;
       pc.j = FE ? Jg + (long long)(lane >> 4) * E + e0n + (lane & (kCH - 1)) : Jg + e0n * 4 + lane;
     }
-    unsigned tk = 0;
-    if (advance) tk = wq.ticket(lane);
+
+    if (!FS && advance) tk = wq.ticket(lane);      // ticket after next; its latency hides under the DMMAs
 
     double acc[kME][kNT][2];
     double accL[2][kME][kNL];      // two partial sums per value: DFMA latency >> 6 chains
@@ -1077,15 +1302,15 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
       auto ktile = [&](auto ktc) {
         constexpr int kt = decltype(ktc)::value;
         const double* bp = sB + (kt * kNT) * 32 + lane;
-  #pragma unroll
+#pragma unroll
         for (int nt = 0; nt < kNT; ++nt) {
           const double b = bp[nt * 32];
-  #pragma unroll
+#pragma unroll
           for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m][kt], b);
         }
         const double2 l01 = *reinterpret_cast<const double2*>(sL + (kt * 4 + t) * 4);
         const double l2 = sL[(kt * 4 + t) * 4 + 2];
-  #pragma unroll
+#pragma unroll
         for (int m = 0; m < kME; ++m) {
           accL[kt & 1][m][0] = fma(a[m][kt], l01.x, accL[kt & 1][m][0]);
           accL[kt & 1][m][1] = fma(a[m][kt], l01.y, accL[kt & 1][m][1]);
@@ -1121,11 +1346,16 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
     } else {
       flush_plain(outg + e0 * 35, stage, e0, E, lane);
     }
-    if (advance) { cur = nxt; nxt = wq.resolve(tk); }
+    if (n == 0) FNSM_TL(4);
+    FNSM_TL_VAL(7, n + 1);
+    if (FS) cur = nchunk;
+    else if (advance) { cur = nchunk; nxt = wq.resolve(tk); }
     fld = nfld;
   }
+  FNSM_TL(5);
   if (lane == 0) tma_store_wait_all();
-  wait_for_previous_kernels();
+  FNSM_TL(6);
+  wait_for_previous_kernels();   // kFlagIndependent: the only wait; otherwise a no-op (the grid ahead has completed)
 }
 
 // ------------------------------------------------------------ launchers ----
@@ -1249,7 +1479,13 @@ inline bool& overlap_with_previous_kernel() {
   thread_local bool flag = false;
   return flag;
 }
-template <class... KArgs, class... Args>
+// `pdl_always` (the three kernels of this file): every launch carries the attribute.  These kernels execute
+// griddepcontrol.wait before their first global access unless kFlagIndependent is set, so the result is ordinary
+// stream order with the launch latency and the on-chip set-up hidden behind the previous kernel's tail (3.6 us
+// between two launches without it, tools/timeline) -- whatever the previous kernel is: a grid that never releases
+// its dependents releases them when it completes.
+inline int independent_flag() { return overlap_with_previous_kernel() ? kFlagIndependent : 0; }
+template <bool pdl_always = false, class... KArgs, class... Args>
 static void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned threads, size_t smem, cudaStream_t st,
                      Args&&... args) {
   cudaLaunchConfig_t lc{};
@@ -1258,7 +1494,7 @@ static void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned threads, 
   lc.dynamicSmemBytes = smem;
   lc.stream = st;
   cudaLaunchAttribute attr[1];
-  if (overlap_with_previous_kernel()) {
+  if (pdl_always || overlap_with_previous_kernel()) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
@@ -1267,54 +1503,63 @@ static void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned threads, 
   cudaLaunchKernelEx(&lc, kernel, std::forward<Args>(args)...);   // errors are picked up by post_launch()
 }
 
+// "Fast start" instantiations (FS = true, see k_div_dmma) for launches that leave a warp only a few work items:
+// there the 4-5 us they save per launch outweigh their slightly slower steady state.  fs_mode 1 / 2
+// force them on / off (cfg->reserved[2] bits 4 / 5: A/B runs and tests).  Compiled for the default warp counts only.
+// Crossovers measured on B200 (profiles/r02_small_e.md): grad ~30 chunks per warp (E ~ 700 k), div ~20 (E ~ 570 k),
+// lift ~8 (E ~ 300 k; its fine queue costs more per item).
+inline bool fast_start(int kind, long long nchunks, int sms, int nw, int fs_mode) {
+  if (fs_mode) return fs_mode == 1;
+  const int below = kind == FNSM_OP_GRAD ? 30 : (kind == FNSM_OP_DIV ? 20 : 8);
+  return nchunks < (long long)below * sms * nw;
+}
+inline int fs_mode_of(const fnsm_cfg* cfg) { return cfg ? ((cfg->reserved[2] >> 4) & 3) : 0; }
+
 // Operands that do not qualify for tensor maps (odd E, a base that is not 16-byte aligned): the TMA = false
 // instantiations, at the default warp counts (div 12 with direct stores, grad 10, lift 16).
 static int launch_dmma_plain(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows,
-                             long long E, int stagger, const DevInfo& di, cudaStream_t st) {
+                             long long E, int stagger, const DevInfo& di, cudaStream_t st, int fs_mode = 0) {
   const long long nchunks = (E + kCH - 1) / kCH;
   const double* J = static_cast<const double*>(jac);
   const double* O = static_cast<const double*>(op);
-  auto grid_for = [&](int nw) {
-    const long long need = (nchunks + nw - 1) / nw;
+  auto grid_for = [&](int nw, long long nitems) {
+    const long long need = (nitems + nw - 1) / nw;
     return (unsigned)(di.sms < need ? di.sms : need);
   };
-  const int flags = stagger << 8;
+  const int flags = (stagger << 8) | independent_flag();
   OpMaps maps{};
-  if (kind == FNSM_OP_DIV) {
-    constexpr int NW = 12;
-    const size_t smem = 8 * ((size_t)DivLayout::B_DOUBLES + (size_t)NW * DivLayout::SLOT_DOUBLES) + 8 * (size_t)NW + 8;
-    auto kernel = k_div_dmma<NW, false, 0, 3, false, false>;
-    if (int rc = set_smem(kernel, smem)) return rc;
-    for (int r = 0; r < nrows; ++r) {
-      launch_k(kernel, grid_for(NW), NW * 32, smem, st, maps, J, O, static_cast<const double*>(rows.field[r]),
-               static_cast<double*>(rows.out[r]), E, flags);
-      if (int rc = post_launch()) return rc;
-    }
-    return FNSM_OK;
-  }
-  if (kind == FNSM_OP_GRAD) {
-    constexpr int NW = 10;
-    const size_t smem = 8 * ((size_t)GradLayout::B_DOUBLES + (size_t)NW * (GradLayout::SLOT_DOUBLES + 3 * OUT_BLOCK)) + 8 * (size_t)NW + 8;
-    auto kernel = k_grad_dmma<NW, false>;
-    if (int rc = set_smem(kernel, smem)) return rc;
-    for (int r = 0; r < nrows; ++r) {
-      launch_k(kernel, grid_for(NW), NW * 32, smem, st, maps, J, O, static_cast<const double*>(rows.field[r]),
-               static_cast<double*>(rows.out[r]), E, flags);
-      if (int rc = post_launch()) return rc;
-    }
-    return FNSM_OK;
+  if (kind == FNSM_OP_DIV || kind == FNSM_OP_GRAD) {
+    const bool is_div = kind == FNSM_OP_DIV;
+    const int NW = is_div ? 12 : 10;
+    const size_t smem = is_div ? 8 * ((size_t)DivLayout::B_DOUBLES + (size_t)NW * DivLayout::SLOT_DOUBLES) + 8 * (size_t)NW + 8
+                               : 8 * ((size_t)GradLayout::B_DOUBLES + (size_t)NW * (GradLayout::SLOT_DOUBLES + 3 * OUT_BLOCK)) + 8 * (size_t)NW + 8;
+    const bool fs = fast_start(kind, nchunks, di.sms, NW, fs_mode);
+    auto go = [&](auto kernel, auto pdl) {
+      if (int rc = set_smem(kernel, smem)) return rc;
+      for (int r = 0; r < nrows; ++r) {
+        launch_k<decltype(pdl)::value>(kernel, grid_for(NW, nchunks), NW * 32, smem, st, maps, J, O,
+                                       static_cast<const double*>(rows.field[r]), static_cast<double*>(rows.out[r]), E, flags);
+        if (int rc = post_launch()) return rc;
+      }
+      return (int)FNSM_OK;
+    };
+    if (is_div) return fs ? go(k_div_dmma<12, false, 0, 3, false, false, true>, std::true_type{})
+                          : go(k_div_dmma<12, false, 0, 3, false, false, false>, std::false_type{});
+    return fs ? go(k_grad_dmma<10, false, true>, std::true_type{}) : go(k_grad_dmma<10, false, false>, std::false_type{});
   }
   constexpr int NW = 16;
   const size_t smem = 8 * ((size_t)LiftLayout::B_DOUBLES + (size_t)NW * (LiftLayout::SLOT_DOUBLES + OUT_BLOCK)) + 8 * (size_t)NW + 8;
   LiftMaps lmaps{};
-  if (kind == FNSM_OP_LIFT_FE) {
-    if (int rc = set_smem(k_lift_dmma<NW, true, false>, smem)) return rc;
-    launch_k(k_lift_dmma<NW, true, false>, grid_for(NW), NW * 32, smem, st, lmaps, J, O, rows, nrows, E, flags);
-  } else {
-    if (int rc = set_smem(k_lift_dmma<NW, false, false>, smem)) return rc;
-    launch_k(k_lift_dmma<NW, false, false>, grid_for(NW), NW * 32, smem, st, lmaps, J, O, rows, nrows, E, flags);
-  }
-  return post_launch();
+  const bool fs = fast_start(kind, nchunks, di.sms, NW, fs_mode);
+  auto go = [&](auto kernel, auto pdl) {
+    if (int rc = set_smem(kernel, smem)) return rc;
+    launch_k<decltype(pdl)::value>(kernel, grid_for(NW, fs ? nchunks * nrows : nchunks), NW * 32, smem, st, lmaps, J, O,
+                                   rows, nrows, E, flags);
+    return post_launch();
+  };
+  const bool fe = kind == FNSM_OP_LIFT_FE;
+  if (fs) return fe ? go(k_lift_dmma<NW, true, false, true>, std::true_type{}) : go(k_lift_dmma<NW, false, false, true>, std::true_type{});
+  return fe ? go(k_lift_dmma<NW, true, false, false>, std::false_type{}) : go(k_lift_dmma<NW, false, false, false>, std::false_type{});
 }
 
 template <int NW>
@@ -1333,12 +1578,14 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
   if (stagger == 0) stagger = kDefaultStagger;
   if (stagger < 0) stagger = 0;                       // negative: off
   if (stagger > (1 << 20)) stagger = 1 << 20;
-  if (!tma) return launch_dmma_plain(kind, jac, op, rows, nrows, E, stagger, di, st);
+  const int fs_mode = fs_mode_of(cfg);
+  if (!tma) return launch_dmma_plain(kind, jac, op, rows, nrows, E, stagger, di, st, fs_mode);
   auto grid_for_items = [&](long long nitems) {
     long long grid = di.sms;                          // one persistent CTA per SM
     const long long need = (nitems + NW - 1) / NW;      // no more CTAs than can be kept busy
     return (unsigned)(grid < need ? grid : need);
   };
+  const bool fs = fast_start(kind, nchunks, di.sms, NW, fs_mode);
 
   if (kind == FNSM_OP_DIV || kind == FNSM_OP_GRAD) {
     const bool is_div = kind == FNSM_OP_DIV;
@@ -1363,49 +1610,62 @@ static int launch_dmma_nw(int kind, const void* jac, const void* op, const Opmat
       if (!ok) {                                        // the driver refused a descriptor: plain producer for this row
         OpmatRows one{};
         one.field[0] = u; one.out[0] = out;
-        if (int rc = launch_dmma_plain(kind, jac, op, one, 1, E, stagger, di, st)) return rc;
+        if (int rc = launch_dmma_plain(kind, jac, op, one, 1, E, stagger, di, st, fs_mode)) return rc;
         continue;
       }
-      const int flags = kFlagTma | (dbg & (kFlagNoLoad | kFlagNoStore)) | (stagger << 8);
+      const int flags = kFlagTma | (dbg & (kFlagNoLoad | kFlagNoStore)) | (stagger << 8) | independent_flag();
+      auto go = [&](auto kernel, auto pdl) {
+        if (int rc = set_smem(kernel, smem)) return rc;
+        launch_k<decltype(pdl)::value>(kernel, grid_for_items(nchunks), threads, smem, st, maps, J, O, u, out, E, flags);
+        return post_launch();
+      };
+      int rc;
       if (is_div) {
-        const int dbgk = cfg ? cfg->reserved[2] : 0;
+        const int dbgk = cfg ? (cfg->reserved[2] & 15) : 0;
         if (staged && NW == 10 && dbgk) {
-#define FNSM_DBG_CASE(M) case M: if (int rc = set_smem(k_div_dmma<10, true, M>, smem)) return rc; \
-          launch_k(k_div_dmma<10, true, M>, grid_for_items(nchunks), threads, smem, st, maps, J, O, u, out, E, flags); break;
+#define FNSM_DBG_CASE(M) case M: rc = go(k_div_dmma<10, true, M>, std::false_type{}); break;
           switch (dbgk) { FNSM_DBG_CASE(1) FNSM_DBG_CASE(2) FNSM_DBG_CASE(4) FNSM_DBG_CASE(3) FNSM_DBG_CASE(5) FNSM_DBG_CASE(6) FNSM_DBG_CASE(7) default: return FNSM_E_BAD_CONFIG; }
 #undef FNSM_DBG_CASE
         } else if (staged) {
-          if (int rc = set_smem(k_div_dmma<NW, true>, smem)) return rc;
-          launch_k(k_div_dmma<NW, true>, grid_for_items(nchunks), threads, smem, st, maps, J, O, u, out, E, flags);
+          rc = go(k_div_dmma<NW, true>, std::false_type{});
         } else {
-          if (int rc = set_smem(k_div_dmma<NW, false>, smem)) return rc;
-          launch_k(k_div_dmma<NW, false>, grid_for_items(nchunks), threads, smem, st, maps, J, O, u, out, E, flags);
+          if constexpr (NW == 12) {
+            rc = fs ? go(k_div_dmma<NW, false, 0, 3, false, true, true>, std::true_type{}) : go(k_div_dmma<NW, false>, std::false_type{});
+          } else {
+            rc = go(k_div_dmma<NW, false>, std::false_type{});
+          }
         }
       } else {
-        if (int rc = set_smem(k_grad_dmma<NW>, smem)) return rc;
-        launch_k(k_grad_dmma<NW>, grid_for_items(nchunks), threads, smem, st, maps, J, O, u, out, E, flags);
+        if constexpr (NW == 10) {
+          rc = fs ? go(k_grad_dmma<NW, true, true>, std::true_type{}) : go(k_grad_dmma<NW>, std::false_type{});
+        } else {
+          rc = go(k_grad_dmma<NW>, std::false_type{});
+        }
       }
-      if (int rc = post_launch()) return rc;
+      if (rc) return rc;
     }
     return FNSM_OK;
   }
   const size_t smem = 8 * ((size_t)LiftLayout::B_DOUBLES + (size_t)NW * (LiftLayout::SLOT_DOUBLES + OUT_BLOCK)) + 8 * (size_t)NW + 8;
   if (smem > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
-  const unsigned grid = grid_for_items(nchunks);
+  const bool fine = NW == 16 && fs;                   // compiled for the default warp count
+  const unsigned grid = grid_for_items(fine ? nchunks * nrows : nchunks);
   LiftMaps maps;
   bool ok = tma && (kind == FNSM_OP_LIFT_FE ? map_erows(&maps.jac, J, E, 4) : map_rows(&maps.jac, J, E, 4));
   for (int r = 0; r < nrows && ok; ++r)
     ok = map_slabs(&maps.in[r], rows.field[r], E, 15, 4) && map_rows(&maps.out[r], rows.out[r], E, 35);
-  if (!ok) return launch_dmma_plain(kind, jac, op, rows, nrows, E, stagger, di, st);
-  const int flags = kFlagTma | (stagger << 8);
-  if (kind == FNSM_OP_LIFT_FE) {
-    if (int rc = set_smem(k_lift_dmma<NW, true>, smem)) return rc;
-    launch_k(k_lift_dmma<NW, true>, grid, threads, smem, st, maps, J, O, rows, nrows, E, flags);
-  } else {
-    if (int rc = set_smem(k_lift_dmma<NW, false>, smem)) return rc;
-    launch_k(k_lift_dmma<NW, false>, grid, threads, smem, st, maps, J, O, rows, nrows, E, flags);
+  if (!ok) return launch_dmma_plain(kind, jac, op, rows, nrows, E, stagger, di, st, fs_mode);
+  const int flags = kFlagTma | (stagger << 8) | independent_flag();
+  auto go = [&](auto kernel, auto pdl) {
+    if (int rc = set_smem(kernel, smem)) return rc;
+    launch_k<decltype(pdl)::value>(kernel, grid, threads, smem, st, maps, J, O, rows, nrows, E, flags);
+    return post_launch();
+  };
+  const bool fe = kind == FNSM_OP_LIFT_FE;
+  if constexpr (NW == 16) {
+    if (fine) return fe ? go(k_lift_dmma<NW, true, true, true>, std::true_type{}) : go(k_lift_dmma<NW, false, true, true>, std::true_type{});
   }
-  return post_launch();
+  return fe ? go(k_lift_dmma<NW, true>, std::false_type{}) : go(k_lift_dmma<NW, false>, std::false_type{});
 }
 
 static int launch_dmma(int kind, const void* jac, const void* op, const OpmatRows& rows, int nrows,

@@ -452,3 +452,46 @@ def test_grad_fp64_second_formulation(cq, n, threads):
     if threads:
         params["threads"] = threads
     check(E.grad(), n, cq, **params)
+
+
+# ---- "fast start" instantiations of the fp64 DMMA kernels (small launches: griddepcontrol.wait up front + programmatic
+# stream serialization, operator staged through shared memory, item-granular lift queue) -- forced on and off at sizes
+# on both sides of the automatic switch, TMA and plain producers
+@pytest.mark.parametrize("fast_start", [1, 2])
+@pytest.mark.parametrize("n", [1, 16, 17, 1000, 1001, 23680, 100001])
+@pytest.mark.parametrize("builder", [E.grad, E.div, E.lift_ef, E.lift_fe])
+def test_dmma_fast_start(cq, n, builder, fast_start):
+    check(builder(), n, cq, variant=1, fast_start=fast_start)
+
+
+@pytest.mark.parametrize("b", [1, 3, 5, 8])
+def test_lift_fast_start_row_counts(cq, b):
+    # the item queue divides by the number of rows with a multiplication
+    check(E.lift_fe(b=b), 4242, cq, variant=1, fast_start=1)
+    check(E.lift_ef(b=b), 4243, cq, variant=1, fast_start=1)
+
+
+@pytest.mark.parametrize("n", [64, 5000, 100000])
+def test_dependent_launches_keep_stream_order(cq, n):
+    """lift -> grad -> lift ... back to back on one stream, each kernel consuming what the one before it wrote: the
+    fast-start kernels are launched with programmatic stream serialization and must not read before the previous
+    grid has completed."""
+    import torch
+
+    lift, grad = E.lift_fe(b=1), E.grad()
+    lin = np_oracle.generate_input_arrays(lift, n, 3)
+    gin = np_oracle.generate_input_arrays(grad, n, 4)
+    dev_l = {k: torch.from_numpy(v).to(cq.torch_device) for k, v in lin.items()}
+    dev_g = {k: torch.from_numpy(v).to(cq.torch_device) for k, v in gin.items()}
+    ex_l = generate_cuda(lift).with_params(variant=1, fast_start=1).executor(cq)
+    ex_g = generate_cuda(grad).with_params(variant=1, fast_start=1).executor(cq)
+    lift_out = torch.zeros((n, 35), dtype=torch.float64, device=cq.torch_device)
+    grad_out = torch.zeros((3, n, 35), dtype=torch.float64, device=cq.torch_device)
+    ref_l = np_oracle.reference_outputs(lift, lin)["_fe_out"]
+    ref_g = np_oracle.reference_outputs(grad, {**gin, "u": ref_l})["_fe_out"]
+    for rep in range(20):
+        lift_out.zero_()            # a foreign kernel ahead of the chain
+        ex_l(cq, **dev_l, _fe_out=lift_out)
+        evt, _ = ex_g(cq, **{**dev_g, "u": lift_out}, _fe_out=grad_out)
+        evt.wait()
+        np_oracle.assert_matches({"_fe_out": grad_out.cpu().numpy()}, {"_fe_out": ref_g}, north_star=True)
