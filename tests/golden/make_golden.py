@@ -22,6 +22,8 @@ Outputs
                      constructions (subscripts string, shape, index lengths,
                      sum indices, output count) and the exception *type* it
                      raises for invalid ones.
+  tccg.json       -- the 48 TCCG contractions as the reference's
+                     ``utils.get_tccg_benchmark`` builds them
   numeric_*.npz   -- inputs drawn by the reference's ``generate_input_arrays``
                      (seed 0) and the outputs of the reference's acceptance
                      expression ``np.einsum(get_subscripts(), ..., optimize="optimal")``
@@ -341,9 +343,28 @@ def numeric_fixture(name: str, long_dim_length: int):
     return payload
 
 
+def tccg_fixture():
+    """What the reference's ``utils.get_tccg_benchmark(i)`` builds for i = 1..48 (reference
+    ``src/feinsum/utils.py:103-233``): subscripts, operand shapes, output shape."""
+    ref_utils = importlib.import_module("feinsum.utils")
+    out = []
+    for i in range(1, 49):
+        e = ref_utils.get_tccg_benchmark(i)
+        out.append({
+            "i": i,
+            "subscripts": e.get_subscripts(),
+            "arg_shapes": [[int(d) for d in e.arg_to_shape[a.name]] for a in e.args[0]],
+            "arg_names": [a.name for a in e.args[0]],
+            "shape": [int(d) for d in e.shape],
+        })
+    return out
+
+
 def main() -> None:
     with open(os.path.join(HERE, "frontend.json"), "w") as fh:
         json.dump(frontend_fixture(), fh, indent=1, sort_keys=True)
+    with open(os.path.join(HERE, "tccg.json"), "w") as fh:
+        json.dump(tccg_fixture(), fh, indent=1, sort_keys=True)
     for name, n in NUMERIC.items():
         np.savez_compressed(os.path.join(HERE, f"numeric_{name}.npz"), **numeric_fixture(name, n))
     print("golden fixtures written to", HERE)

@@ -131,3 +131,23 @@ def test_immutable_map():
     assert m.set("a", 5)["a"] == 5 and "a" not in m.delete("a")
     with pytest.raises(AttributeError):
         m.x = 1
+
+
+def test_tccg_benchmark_getter():
+    """reference test/test_feinsum.py:286-288, plus every field against what the reference's own getter
+    builds (tests/golden/tccg.json, written by make_golden.py from src/feinsum/utils.py:103-233)."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "tccg.json")) as fh:
+        cases = json.load(fh)
+    assert [c["i"] for c in cases] == list(range(1, 49))
+    for c in cases:
+        e = f.utils.get_tccg_benchmark(c["i"])
+        assert isinstance(e, f.BatchedEinsum)
+        assert e.get_subscripts() == c["subscripts"]
+        assert [a.name for a in e.args[0]] == c["arg_names"]
+        assert [[int(d) for d in e.arg_to_shape[n]] for n in c["arg_names"]] == c["arg_shapes"]
+        assert [int(d) for d in e.shape] == c["shape"]
+        assert all(np.dtype(dt) == np.float64 for dt in e.arg_to_dtype.values())
+    assert np.dtype(f.utils.get_tccg_benchmark(3, "float32").arg_to_dtype["A"]) == np.float32
+    for bad in (0, 49, -1):
+        with pytest.raises(ValueError):
+            f.utils.get_tccg_benchmark(bad)

@@ -495,3 +495,11 @@ def test_dependent_launches_keep_stream_order(cq, n):
         evt, _ = ex_g(cq, **{**dev_g, "u": lift_out}, _fe_out=grad_out)
         evt.wait()
         np_oracle.assert_matches({"_fe_out": grad_out.cpu().numpy()}, {"_fe_out": ref_g}, north_star=True)
+
+
+@pytest.mark.parametrize("i", [1, 9, 30, 48])
+def test_tccg_contractions_run_on_the_generic_kernel(cq, i):
+    # reference utils.get_tccg_benchmark (src/feinsum/utils.py:206-233): fixed-size two-operand contractions
+    e = f.utils.get_tccg_benchmark(i)
+    assert generate_cuda(e).plan.kernel_id == "generic"
+    check(e, 1, cq, seed=i)
