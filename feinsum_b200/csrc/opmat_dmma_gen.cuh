@@ -87,9 +87,8 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
   constexpr int NIN = L::IN_DOUBLES / 32, NJR = (L::J_DOUBLES + 31) / 32;
   static_assert(L::IN_DOUBLES % 32 == 0, "slot size must be a multiple of the warp size");
   double rin[NIN], rj[NJR];
-  auto fetch = [&](long long item) {
-    const long long chunk = chunk0 + (item / nrows) * wstride;
-    const int row = (int)(item % nrows);
+  // (chunk, row) of an item advance by counting: a 64-bit division per item costs as much as its DMMAs
+  auto fetch = [&](long long chunk, int row) {
     const long long e0 = chunk * L::CH;
     const int ne = (int)((E - e0 < L::CH) ? (E - e0) : L::CH);
     const double* __restrict__ in = static_cast<const double*>(rows.field[row]);
@@ -114,10 +113,13 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
       }
     }
   };
-  if (nitems > 0) fetch(0);
+  if (nitems > 0) fetch(chunk0, 0);
+  long long chunk = chunk0;
+  int row = 0;
   for (long long item = 0; item < nitems; ++item) {
-    const long long chunk = chunk0 + (item / nrows) * wstride;
-    const int row = (int)(item % nrows);
+    // the item after this one
+    const int row_n = row + 1 == nrows ? 0 : row + 1;
+    const long long chunk_n = row_n == 0 ? chunk + wstride : chunk;
     const long long e0 = chunk * L::CH;
     const int ne = (int)((E - e0 < L::CH) ? (E - e0) : L::CH);
     double* __restrict__ out = static_cast<double*>(rows.out[row]);
@@ -135,7 +137,7 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
           }
         }
       }
-      if (item + 1 < nitems) fetch(item + 1);
+      if (item + 1 < nitems) fetch(chunk_n, row_n);
       __syncwarp();
       // ---- A fragments: lane (g, t) holds rows el = g + 8 m, k = (kt, t) ----
       double a[L::ME][L::KT];
@@ -214,6 +216,8 @@ k_opmat_dmma_gen(const double* __restrict__ Jg, const double* __restrict__ Og, c
       }
       __syncwarp();                                       // slot and stage are rewritten by the next item
     }
+    chunk = chunk_n;
+    row = row_n;
   }
 }
 

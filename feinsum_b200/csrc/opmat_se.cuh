@@ -68,9 +68,8 @@ k_se_dmma_gen(const double* __restrict__ Og, const __grid_constant__ SeRows rows
   // software pipeline: item n + 1 travels global -> registers while item n is computed
   constexpr int NIN = (L::IN_DOUBLES + 31) / 32, NJR = (L::J_DOUBLES + 31) / 32;
   double rin[NIN], rj[NJR];
-  auto fetch = [&](long long item) {
-    const long long chunk = chunk0 + (item / nrows) * wstride;
-    const int row = (int)(item % nrows);
+  // (chunk, row) of an item advance by counting: a 64-bit division per item costs as much as its DMMAs
+  auto fetch = [&](long long chunk, int row) {
     const long long e0 = chunk * L::CH;
     const int ne = (int)((E - e0 < L::CH) ? (E - e0) : L::CH);
     const double* __restrict__ in = static_cast<const double*>(rows.field[row]);
@@ -91,10 +90,13 @@ k_se_dmma_gen(const double* __restrict__ Og, const __grid_constant__ SeRows rows
       }
     }
   };
-  if (nitems > 0) fetch(0);
+  if (nitems > 0) fetch(chunk0, 0);
+  long long chunk = chunk0;
+  int row = 0;
   for (long long item = 0; item < nitems; ++item) {
-    const long long chunk = chunk0 + (item / nrows) * wstride;
-    const int row = (int)(item % nrows);
+    // the item after this one
+    const int row_n = row + 1 == nrows ? 0 : row + 1;
+    const long long chunk_n = row_n == 0 ? chunk + wstride : chunk;
     const long long e0 = chunk * L::CH;
     const int ne = (int)((E - e0 < L::CH) ? (E - e0) : L::CH);
     double* __restrict__ out = static_cast<double*>(rows.out[row]);
@@ -104,7 +106,7 @@ k_se_dmma_gen(const double* __restrict__ Og, const __grid_constant__ SeRows rows
 #pragma unroll
     for (int q = 0; q < NJR; ++q)
       if (lane + 32 * q < L::J_DOUBLES) sJ[lane + 32 * q] = rj[q];
-    if (item + 1 < nitems) fetch(item + 1);
+    if (item + 1 < nitems) fetch(chunk_n, row_n);
     __syncwarp();
     // ---- A fragments: lane (g, t) holds rows el = g + 8 m, k = (kt, t): w = J[s][el] u[el][j] ----
     double a[L::ME][L::KT];
@@ -156,6 +158,8 @@ k_se_dmma_gen(const double* __restrict__ Og, const __grid_constant__ SeRows rows
       stg_stream(out + e0 * NI + idx, stage[el * L::PITCH + i]);
     }
     __syncwarp();                                         // slot and stage are rewritten by the next item
+    chunk = chunk_n;
+    row = row_n;
   }
 }
 

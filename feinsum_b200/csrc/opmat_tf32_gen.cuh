@@ -71,9 +71,8 @@ k_opmat_tf32_gen(const float* __restrict__ Jg, const float* __restrict__ Og, con
   constexpr int NIN = L::IN_FLOATS / 32, NJR = (L::J_FLOATS + 31) / 32;
   static_assert(L::IN_FLOATS % 32 == 0, "slot size must be a multiple of the warp size");
   float rin[NIN], rj[NJR];
-  auto fetch = [&](long long item) {
-    const long long chunk = chunk0 + (item / nrows) * wstride;
-    const int row = (int)(item % nrows);
+  // (chunk, row) of an item advance by counting: a 64-bit division per item costs as much as its DMMAs
+  auto fetch = [&](long long chunk, int row) {
     const long long e0 = chunk * kCH;
     const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
     const float* __restrict__ in = static_cast<const float*>(rows.field[row]);
@@ -98,10 +97,13 @@ k_opmat_tf32_gen(const float* __restrict__ Jg, const float* __restrict__ Og, con
       }
     }
   };
-  if (nitems > 0) fetch(0);
+  if (nitems > 0) fetch(chunk0, 0);
+  long long chunk = chunk0;
+  int row = 0;
   for (long long item = 0; item < nitems; ++item) {
-    const long long chunk = chunk0 + (item / nrows) * wstride;
-    const int row = (int)(item % nrows);
+    // the item after this one
+    const int row_n = row + 1 == nrows ? 0 : row + 1;
+    const long long chunk_n = row_n == 0 ? chunk + wstride : chunk;
     const long long e0 = chunk * kCH;
     const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
     float* __restrict__ out = static_cast<float*>(rows.out[row]);
@@ -117,7 +119,7 @@ k_opmat_tf32_gen(const float* __restrict__ Jg, const float* __restrict__ Og, con
         }
       }
     }
-    if (item + 1 < nitems) fetch(item + 1);
+    if (item + 1 < nitems) fetch(chunk_n, row_n);
     __syncwarp();
     // ---- A fragments (m16n8k8): a[2c + h] = A[row g + 8h][k = (kt, t + 4c)], split hi / lo ----
     uint32_t ahi[L::KT][4], alo[L::KT][4];
@@ -197,6 +199,8 @@ k_opmat_tf32_gen(const float* __restrict__ Jg, const float* __restrict__ Og, con
       }
     }
     __syncwarp();                                         // slot and stage are rewritten by the next item
+    chunk = chunk_n;
+    row = row_n;
   }
 }
 
