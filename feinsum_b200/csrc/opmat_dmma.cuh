@@ -210,6 +210,19 @@ __device__ __forceinline__ void stage_operator_raw(double* scratch, const double
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void stage_operator_raw_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// 1-D bulk copy global -> shared with completion on an mbarrier: both addresses 16-byte aligned, size a multiple of 16
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// ... and shared -> global (bulk async-group of the issuing thread, like the tensor stores)
+__device__ __forceinline__ void bulk_store(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+// 1 if p is 8 (mod 16): a run of doubles that starts there is copied from one double earlier (and lands one double
+// later in its shared-memory region, which has two doubles of headroom)
+__device__ __forceinline__ int odd8(const void* p) { return (int)((reinterpret_cast<uintptr_t>(p) >> 3) & 1u); }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
@@ -316,97 +329,83 @@ struct DivLayoutT {
   static constexpr int U_SLAB = kCH * 35;                            // doubles per x
   static constexpr int SLOT_DOUBLES = NX * U_SLAB + 3 * NX * kCH;    // NX = 3: 1824 -> 14592 B
   static constexpr uint32_t SLOT_BYTES = SLOT_DOUBLES * 8;
+  static constexpr int SLOT_DOUBLES_BULK = SLOT_DOUBLES + 2 * NX;    // TMA = false: two doubles of headroom per slab
 };
 using DivLayout = DivLayoutT<3>;
 
 // ES (NX = 1 only): the geometric factors are laid out J(E, 3) -- "es,sij,ej->ei", reference
 // examples/dg_wave_div.py:14 -- instead of J(3, E); the slot then holds them as [el][s]
-// plain (non-TMA) producer of one divergence chunk.  It lives in its own kernel instantiation (TMA = false): compiled
-// into the TMA kernels as a cold branch -- inline or as a call -- it cost them 2-5 % (A/B on one box, profiles/r02_ab_dmma.md)
+//
+// Producer for operands that do not qualify for tensor maps (odd E: every other slab / Jacobian row starts 8 (mod 16);
+// or a view whose base does).  It lives in its own kernel instantiation (TMA = false): compiled into the TMA kernels
+// as a cold branch -- inline or as a call -- it cost them 2-5 % (A/B on one box, profiles/r02_ab_dmma.md).
+//   * a slab of a chunk is one contiguous run of 16 x 35 doubles whose offset inside the slab is a multiple of 16
+//     bytes, so it travels as ONE 1-D bulk copy (cp.async.bulk); when the slab starts 8 (mod 16) the copy starts one
+//     double early and is 16 bytes longer -- the slot's slab regions have two doubles of headroom (pitch U_SLAB + 2)
+//     and the consumer reads slab x from s + x * pitch + sh[x].  Round 2's first version moved the slabs with 8-byte
+//     cp.async from every lane, woven into the DMMA stream: 57 LDGSTS per lane and chunk against 3 bulk copies from
+//     one lane -- in an issue-bound kernel that was the difference to the TMA instantiation (profiles/r02_cliff.md);
+//   * the Jacobian entries (16 doubles per row) stay 8-byte cp.async: 5 per lane;
+//   * the LAST chunk is copied element-wise: it may be partial, and a shifted bulk copy of it would read 8 bytes
+//     past the end of the array.  (Inline: out of line -- a call -- the kernel lost 7 %; with byte counts computed
+//     from the number of valid elements instead of this branch it lost 10 %.  ptxas' allocation of the hot loop
+//     decides, not the instruction count.)
+// The slot's barrier counts 33 arrivals: the 32 lanes through their cp.async groups + the elected lane's expect_tx
+// (or plain) arrival.
 template <int NX, bool ES>
-__device__ __forceinline__ void div_issue_plain(double* s, uint64_t* bar, const double* __restrict__ Jg,
-                                             const double* __restrict__ ug, long long e0, long long E, int lane) {
+__device__ __forceinline__ void div_issue_bulk(double* s, uint64_t* bar, const double* __restrict__ Jg,
+                                               const double* __restrict__ ug, long long chunk, long long nchunks,
+                                               long long E, int lane, const int (&sh)[NX]) {
   using L = DivLayoutT<NX>;
-    // rows of elements past E are not copied: they hold stale (finite or not) data, are computed -- the rows of a
-    // DMMA tile are independent -- and never stored
-    // fully unrolled with immediate offsets: a rolled loop serialises on the address register of each LDGSTS
-    // (long-scoreboard release), ~57 round trips per chunk (profiles/r02_ncu_div_p4_odd.txt)
-    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-#pragma unroll
-    for (int x = 0; x < NX; ++x)
-      cp_async_run<L::U_SLAB>(s + x * L::U_SLAB, ug + ((long long)x * E + e0) * 35, ne * 35, lane);
-    if (ES) {
-#pragma unroll
-      for (int q = 0; q < (3 * kCH + 31) / 32; ++q)
-        if (lane + 32 * q < 3 * ne) cp_async8(s + NX * L::U_SLAB + lane + 32 * q, Jg + e0 * 3 + lane + 32 * q);
-    } else {
-      // k = lane + 32 q  <->  row xr = k / 16 = (lane >> 4) + 2 q, element el = lane & 15
-      const int el = lane & (kCH - 1);
-      const double* src = Jg + (long long)(lane >> 4) * E + e0 + el;
-#pragma unroll
-      for (int q = 0; q < (3 * NX * kCH + 31) / 32; ++q)
-        if (lane + 32 * q < 3 * NX * kCH && el < ne) cp_async8(s + NX * L::U_SLAB + lane + 32 * q, src + (long long)(2 * q) * E);
-    }
-    cp_async_arrive_noinc(bar);
-}
-
-// The plain producer SPREAD over the DMMA stream.  Issued as one burst (div_issue_plain), the ~60 LDGSTS of a chunk
-// pile up in the MIO queue in front of the other warps' B-fragment LDS and their DMMA streams stall on the short
-// scoreboard (17.6 % of the stall samples against 5.7 % with TMA, profiles/r02_ncu_div_p4_odd.txt).  Two copies
-// behind every k-tile's eight DMMAs keep the queue shallow; the slot was consumed into registers before the stream
-// starts, so it can be refilled piecemeal.
-template <int NX>
-struct DivPlainCtx {
-  uint32_t s;                 // shared address of the slot + lane * 8
-  const double* u[NX];        // global address of slab x of the next chunk + lane
-  const double* j;            // J: address of row (lane >> 4), element e0 + (lane & 15)  [ES: e0 * 3 + lane]
-  long long E2;               // 2 E: stride between the rows two apart
-  int nvalid, ne, lane;       // valid doubles per slab, valid elements
-  bool active;
-};
-template <int NX, bool ES, int KTI>
-__device__ __forceinline__ void div_plain_step(const DivPlainCtx<NX>& c) {
-  using L = DivLayoutT<NX>;
-  constexpr int ROWS = (L::U_SLAB + 31) / 32;                 // 18 rows of 32 doubles per slab
-  constexpr int NU = NX * ROWS, PER = (NU + L::KT - 1) / L::KT;
-  if (!c.active) return;
-  constexpr int C0 = KTI * PER, C1 = C0 + 1;
-  if constexpr (C0 < NU) {
-    constexpr int x = C0 / ROWS, q = C0 % ROWS;
-    if (c.lane + 32 * q < c.nvalid) cp_async8_imm<(x * L::U_SLAB + 32 * q) * 8, 32 * q * 8>(c.s, c.u[x]);
-  }
-  if constexpr (PER > 1 && C1 < NU) {
-    constexpr int x = C1 / ROWS, q = C1 % ROWS;
-    if (c.lane + 32 * q < c.nvalid) cp_async8_imm<(x * L::U_SLAB + 32 * q) * 8, 32 * q * 8>(c.s, c.u[x]);
-  }
-  // the Jacobian rows ride on the first few k-tiles
-  constexpr int NJQ = (3 * NX * kCH + 31) / 32;
-  if constexpr (KTI < NJQ) {
-    if (ES) {
-      if (c.lane + 32 * KTI < 3 * c.ne) cp_async8_imm<(NX * L::U_SLAB + 32 * KTI) * 8, 32 * KTI * 8>(c.s, c.j);
-    } else if (c.lane + 32 * KTI < 3 * NX * kCH && (c.lane & (kCH - 1)) < c.ne) {
-      cp_async8_imm<(NX * L::U_SLAB + 32 * KTI) * 8, 0>(c.s, c.j + (long long)KTI * c.E2);
-    }
-  }
-}
-
-template <int NX, bool ES = false, bool TMA = true>
-__device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps* maps,
-                                          const double* __restrict__ Jg, const double* __restrict__ ug,
-                                          long long chunk, long long E, int lane) {
-  using L = DivLayoutT<NX>;
+  constexpr int PITCH = L::U_SLAB + 2;
   const long long e0 = chunk * kCH;
-  if constexpr (TMA) {
+  // rows of elements past E are not copied: they hold stale (finite or not) data, are computed -- the rows of a
+  // DMMA tile are independent -- and never stored
+  const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+  if (chunk + 1 < nchunks) {
     if (elect_one()) {
       fence_proxy_async();
-      mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
-      if (NX == 3) tma_load_3d(s, &maps->in, 0, (int)(chunk * (kCH / 2)), 0, bar);   // u[0..2][16 el][35]
-      else         tma_load_2d(s, &maps->in, 0, (int)(chunk * (kCH / 2)), bar);      // u[16 el][35]
-      if (ES) tma_load_2d(s + NX * L::U_SLAB, &maps->jac, 0, (int)(chunk * (kCH / 2)), bar);   // J[16 el][3]
-      else    tma_load_2d(s + NX * L::U_SLAB, &maps->jac, (int)e0, 0, bar);      // J[3 NX][16 el]
+      uint32_t bytes = 0;
+#pragma unroll
+      for (int x = 0; x < NX; ++x) bytes += L::U_SLAB * 8 + 16 * sh[x];
+      mbar_arrive_expect_tx(bar, bytes);
+#pragma unroll
+      for (int x = 0; x < NX; ++x)
+        bulk_load(s + x * PITCH, ug + ((long long)x * E + e0) * 35 - sh[x], L::U_SLAB * 8 + 16 * sh[x], bar);
     }
   } else {
-    div_issue_plain<NX, ES>(s, bar, Jg, ug, e0, E, lane);
+#pragma unroll
+    for (int x = 0; x < NX; ++x)
+      cp_async_run<L::U_SLAB>(s + x * PITCH + sh[x], ug + ((long long)x * E + e0) * 35, ne * 35, lane);
+    if (elect_one()) mbar_arrive(bar);
+  }
+  double* sJ = s + NX * PITCH;
+  if (ES) {
+#pragma unroll
+    for (int q = 0; q < (3 * kCH + 31) / 32; ++q)
+      if (lane + 32 * q < 3 * ne) cp_async8(sJ + lane + 32 * q, Jg + e0 * 3 + lane + 32 * q);
+  } else {
+    // k = lane + 32 q  <->  row xr = k / 16 = (lane >> 4) + 2 q, element el = lane & 15
+    const int el = lane & (kCH - 1);
+    const double* src = Jg + (long long)(lane >> 4) * E + e0 + el;
+#pragma unroll
+    for (int q = 0; q < (3 * NX * kCH + 31) / 32; ++q)
+      if (lane + 32 * q < 3 * NX * kCH && el < ne) cp_async8(sJ + lane + 32 * q, src + (long long)(2 * q) * E);
+  }
+  cp_async_arrive_noinc(bar);
+}
+
+template <int NX, bool ES = false>
+__device__ __forceinline__ void div_issue(double* s, uint64_t* bar, const OpMaps* maps, long long chunk) {
+  using L = DivLayoutT<NX>;
+  const long long e0 = chunk * kCH;
+  if (elect_one()) {
+    fence_proxy_async();
+    mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
+    if (NX == 3) tma_load_3d(s, &maps->in, 0, (int)(chunk * (kCH / 2)), 0, bar);   // u[0..2][16 el][35]
+    else         tma_load_2d(s, &maps->in, 0, (int)(chunk * (kCH / 2)), bar);      // u[16 el][35]
+    if (ES) tma_load_2d(s + NX * L::U_SLAB, &maps->jac, 0, (int)(chunk * (kCH / 2)), bar);   // J[16 el][3]
+    else    tma_load_2d(s + NX * L::U_SLAB, &maps->jac, (int)e0, 0, bar);      // J[3 NX][16 el]
   }
 }
 
@@ -435,24 +434,33 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   double* sB = reinterpret_cast<double*>(smem_raw);
   double* sL = sB + L::B_MAIN;
   double* slots = sB + L::B_DOUBLES;
-  double* stages = slots + (size_t)NW * L::SLOT_DOUBLES;
+  constexpr int PITCH = L::U_SLAB + (TMA ? 0 : 2);                  // bulk producer: two doubles of headroom per slab
+  constexpr int SLOT = L::SLOT_DOUBLES + (TMA ? 0 : 2 * NX);
+  double* stages = slots + (size_t)NW * SLOT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (STAGED ? (size_t)NW * OUT_BLOCK : 0));
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
-    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], TMA ? 1 : 32);   // plain producer: every lane arrives
+    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], TMA ? 1 : 33);   // bulk producer: 32 lanes + the elected one
     *work_ctr = 0u;
     mbar_fence_init();
   }
   __syncthreads();
   FNSM_TL_VAL(0, tl_entry_);
 
-  double* s = slots + (size_t)warp * L::SLOT_DOUBLES;
+  double* s = slots + (size_t)warp * SLOT;
   double* stage = stages + (size_t)warp * (STAGED ? OUT_BLOCK : 0);
   uint64_t* bar = &bars[warp];
-  const double* sJ = s + NX * L::U_SLAB;
+  const double* sJ = s + NX * PITCH;
   const long long nchunks = (E + kCH - 1) / kCH;
+  int sh[NX];                                                       // bulk producer: slab x sits at s + x PITCH + sh[x]
+#pragma unroll
+  for (int x = 0; x < NX; ++x) sh[x] = TMA ? 0 : odd8(ug + (long long)x * E * 35);
+  auto issue = [&](long long chunk) {
+    if constexpr (TMA) div_issue<NX, ES>(s, bar, &maps, chunk);
+    else               div_issue_bulk<NX, ES>(s, bar, Jg, ug, chunk, nchunks, E, lane, sh);
+  };
   const WorkQueue wq{work_ctr, nchunks};
   const int g = lane >> 2, t = lane & 3, tpad = t < 3 ? t : 2;
 
@@ -467,18 +475,18 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
   // The raw operator is staged through the slots of the last NSCR warps (there is no other free shared memory);
   // those warps issue their first loads once the tables are in fragment order.
   constexpr int RAW = 3 * 35 * 35;
-  constexpr int NSCR = (RAW + L::SLOT_DOUBLES - 1) / L::SLOT_DOUBLES;
+  constexpr int NSCR = (RAW + SLOT - 1) / SLOT;
   constexpr bool kRawStage = FS && NSCR <= NW;
   static_assert(!FS || kRawStage, "fast start needs NSCR slots of scratch");
   const bool late = kRawStage && warp >= NW - NSCR;
-  if constexpr (kRawStage) stage_operator_raw<RAW, NW * 32>(slots + (size_t)(NW - NSCR) * L::SLOT_DOUBLES, Dg);
-  if (cur < nchunks && !dbg_noload && !late) div_issue<NX, ES, TMA>(s, bar, &maps, Jg, ug, cur, E, lane);
+  if constexpr (kRawStage) stage_operator_raw<RAW, NW * 32>(slots + (size_t)(NW - NSCR) * SLOT, Dg);
+  if (cur < nchunks && !dbg_noload && !late) issue(cur);
   // operator tables are staged while the first TMA loads are in flight
   // main operator fragments, column tiles in pairs so that one LDS.128 feeds two of them:
   // sB[((kt*2 + p)*32 + lane)*2 + h] = D[r][8(2p+h)+g][4jq+t]
   // left-over dofs: sL[(kt*4 + t)*4 + d] = D[r][32+d][4jq+t]
   if constexpr (kRawStage) {
-    const double* raw = slots + (size_t)(NW - NSCR) * L::SLOT_DOUBLES;
+    const double* raw = slots + (size_t)(NW - NSCR) * SLOT;
     stage_operator_raw_wait();
     FNSM_TL(8);
     __syncthreads();
@@ -504,7 +512,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
       sL[idx] = (d < kNL && j < 35) ? raw[(r * 35 + 32 + d) * 35 + j] : 0.0;
     }
     __syncthreads();
-    if (cur < nchunks && !dbg_noload && late) div_issue<NX, ES, TMA>(s, bar, &maps, Jg, ug, cur, E, lane);
+    if (cur < nchunks && !dbg_noload && late) issue(cur);
   } else {
     _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
     for (int idx = threadIdx.x; idx < L::B_MAIN; idx += blockDim.x) {
@@ -548,7 +556,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
         const int j = jq == 8 ? 32 + tpad : 4 * jq + t;
         double ux[NX];
 #pragma unroll
-        for (int x = 0; x < NX; ++x) ux[x] = s[x * L::U_SLAB + el * 35 + j];
+        for (int x = 0; x < NX; ++x) ux[x] = s[x * PITCH + sh[x] + el * 35 + j];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           if (NX == 3) a[m][3 * jq + r] = fma(Jr[2 * NX + r], ux[NX - 1], fma(Jr[NX + r], ux[NX > 1 ? 1 : 0], Jr[r] * ux[0]));
@@ -558,21 +566,7 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
     }
     __syncwarp();                                  // every lane is done reading the slot
     if (FS) nxt = wq.resolve(tk);
-    DivPlainCtx<NX> pc;
-    if constexpr (TMA) {
-      if (nxt < nchunks && !dbg_noload) div_issue<NX, ES, TMA>(s, bar, &maps, Jg, ug, nxt, E, lane);
-    } else {                                       // plain producer: spread over the DMMA stream below
-      const long long e0n = nxt * kCH;
-      pc.active = nxt < nchunks;
-      pc.ne = (int)((E - e0n < kCH) ? (E - e0n) : kCH);
-      pc.nvalid = pc.ne * 35;
-      pc.lane = lane;
-      pc.s = smem_u32(s + lane);
-      pc.E2 = 2 * E;
-#pragma unroll
-      for (int x = 0; x < NX; ++x) pc.u[x] = ug + ((long long)x * E + e0n) * 35 + lane;
-      pc.j = ES ? Jg + e0n * 3 + lane : Jg + (long long)(lane >> 4) * E + e0n + (lane & (kCH - 1));
-    }
+    if (nxt < nchunks && !dbg_noload) issue(nxt);
     if (!FS) tk = wq.ticket(lane);                // ticket after next; its latency hides under the DMMAs
 
     // ---- DMMA stream ----
@@ -584,38 +578,21 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
     // B fragments are fetched one k-tile ahead of their DMMAs (ptxas otherwise funnels every fragment
     // through one register pair and exposes the LDS latency to each pair of DMMAs)
     const uint32_t bB = smem_u32(sB) + lane * 16, bL = smem_u32(sL) + t * 32;
-    if constexpr (TMA) {
-      double2 bq[2][2];
-      bq[0][0] = lds_v2(bB); bq[0][1] = lds_v2(bB + 512);
+    {
+    double2 bq[2][2];
+    bq[0][0] = lds_v2(bB); bq[0][1] = lds_v2(bB + 512);
 #pragma unroll
-      for (int kt = 0; kt < L::KT; ++kt) {
-        const int c = kt & 1, nx = c ^ 1;
-        if (kt + 1 < L::KT) { bq[nx][0] = lds_v2(bB + (kt + 1) * 1024); bq[nx][1] = lds_v2(bB + (kt + 1) * 1024 + 512); }
+    for (int kt = 0; kt < L::KT; ++kt) {
+      const int c = kt & 1, nx = c ^ 1;
+      if (kt + 1 < L::KT) { bq[nx][0] = lds_v2(bB + (kt + 1) * 1024); bq[nx][1] = lds_v2(bB + (kt + 1) * 1024 + 512); }
 #pragma unroll
-        for (int m = 0; m < kME; ++m) {
-          dmma884(acc[m][0], a[m][kt], bq[c][0].x);
-          dmma884(acc[m][1], a[m][kt], bq[c][0].y);
-          dmma884(acc[m][2], a[m][kt], bq[c][1].x);
-          dmma884(acc[m][3], a[m][kt], bq[c][1].y);
-        }
+      for (int m = 0; m < kME; ++m) {
+        dmma884(acc[m][0], a[m][kt], bq[c][0].x);
+        dmma884(acc[m][1], a[m][kt], bq[c][0].y);
+        dmma884(acc[m][2], a[m][kt], bq[c][1].x);
+        dmma884(acc[m][3], a[m][kt], bq[c][1].y);
       }
-    } else {
-      // the same stream with the next chunk's copies woven in (compile-time k-tile index: immediate offsets)
-      double2 bq[2][2];
-      bq[0][0] = lds_v2(bB); bq[0][1] = lds_v2(bB + 512);
-      static_for<L::KT>([&](auto ktc) {
-        constexpr int kt = decltype(ktc)::value, c = kt & 1, nx = c ^ 1;
-        if (kt + 1 < L::KT) { bq[nx][0] = lds_v2(bB + (kt + 1) * 1024); bq[nx][1] = lds_v2(bB + (kt + 1) * 1024 + 512); }
-#pragma unroll
-        for (int m = 0; m < kME; ++m) {
-          dmma884(acc[m][0], a[m][kt], bq[c][0].x);
-          dmma884(acc[m][1], a[m][kt], bq[c][0].y);
-          dmma884(acc[m][2], a[m][kt], bq[c][1].x);
-          dmma884(acc[m][3], a[m][kt], bq[c][1].y);
-        }
-        div_plain_step<NX, ES, kt>(pc);
-      });
-      if (pc.active) cp_async_arrive_noinc(bar);
+    }
     }
     const long long e0 = cur * kCH;
     // ---- dofs 0..31 leave the registers first ... ----
@@ -738,85 +715,72 @@ struct GradLayout {
   static constexpr uint32_t SLOT_BYTES = SLOT_DOUBLES * 8;
 };
 
-__device__ __forceinline__ void grad_issue_plain(double* s, uint64_t* bar, const double* __restrict__ Jg,
-                                              const double* __restrict__ ug, long long e0, long long E, int lane) {
+// bulk producer of a grad chunk (see div_issue_bulk): u as one 1-D bulk copy into a region with two doubles of
+// headroom (data at s + shu), the 9 x 16 Jacobian entries by 8-byte cp.async from every lane, 33 arrivals
+__device__ __forceinline__ void grad_issue_bulk(double* s, uint64_t* bar, const double* __restrict__ Jg,
+                                                const double* __restrict__ ug, long long chunk, long long nchunks,
+                                                long long E, int lane, int shu) {
   using L = GradLayout;
-    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-    cp_async_run<L::U_SLAB>(s, ug + e0 * 35, ne * 35, lane);
-    {
-      const int el = lane & (kCH - 1);
-      const double* src = Jg + (long long)(lane >> 4) * E + e0 + el;
-#pragma unroll
-      for (int q = 0; q < (9 * kCH + 31) / 32; ++q)
-        if (lane + 32 * q < 9 * kCH && el < ne) cp_async8(s + L::U_SLAB + lane + 32 * q, src + (long long)(2 * q) * E);
+  const long long e0 = chunk * kCH;
+  const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+  if (chunk + 1 < nchunks) {
+    if (elect_one()) {
+      fence_proxy_async();
+      mbar_arrive_expect_tx(bar, L::U_SLAB * 8 + 16 * shu);
+      bulk_load(s, ug + e0 * 35 - shu, L::U_SLAB * 8 + 16 * shu, bar);
     }
-    cp_async_arrive_noinc(bar);
+  } else {                                   // last chunk: element-wise (partial; end of the array)
+    cp_async_run<L::U_SLAB>(s + shu, ug + e0 * 35, ne * 35, lane);
+    if (elect_one()) mbar_arrive(bar);
+  }
+  {
+    const int el = lane & (kCH - 1);
+    const double* src = Jg + (long long)(lane >> 4) * E + e0 + el;
+#pragma unroll
+    for (int q = 0; q < (9 * kCH + 31) / 32; ++q)
+      if (lane + 32 * q < 9 * kCH && el < ne) cp_async8(s + L::U_SLAB + 2 + lane + 32 * q, src + (long long)(2 * q) * E);
+  }
+  cp_async_arrive_noinc(bar);
 }
 
 // TMA instantiation: `tma_ok` = the launch flag kFlagTma.  With it clear the slot is filled synchronously (LDG -> STS ->
 // one arrival: round 1's plain path).  The library's launchers never clear it -- operands that do not qualify for
-// tensor maps go to the TMA = false instantiation (cp.async producer) -- but the branch stays: with it compiled out,
+// tensor maps go to the TMA = false instantiation (bulk producer) -- but the branch stays: with it compiled out,
 // ptxas allocates / schedules the hot loop of the grad and lift kernels 1-3 % slower (A/B of both builds on one box,
 // profiles/r02_ab_dmma.md).  It costs nothing at run time (one uniform predicate per work item).
-// plain producer of a grad chunk in five bursts, one behind each group of column tiles: 18 rows of 32 doubles of u
-// (four per burst) + 5 of J (one per burst)
-struct GradPlainCtx {
-  uint32_t s;
-  const double* u;            // next chunk + lane
-  const double* j;            // row (lane >> 4), element e0 + (lane & 15)
-  long long E2;
-  int nvalid, ne, lane;
-  bool active;
-};
-template <int G>
-__device__ __forceinline__ void grad_plain_step(const GradPlainCtx& c) {
-  using L = GradLayout;
-  constexpr int ROWS = (L::U_SLAB + 31) / 32;                   // 18
-  if (!c.active) return;
-#pragma unroll
-  for (int h = 0; h < 4; ++h) {
-    constexpr int q0 = 4 * G;
-    const int q = q0 + h;
-    if (q < ROWS && c.lane + 32 * q < c.nvalid) cp_async8_rr(c.s + 32 * q * 8, c.u + 32 * q);
-  }
-  if (c.lane + 32 * G < 9 * kCH && (c.lane & (kCH - 1)) < c.ne)
-    cp_async8_rr(c.s + (L::U_SLAB + 32 * G) * 8, c.j + (long long)G * c.E2);
-}
-
-template <bool TMA>
 __device__ __forceinline__ void grad_issue(double* s, uint64_t* bar, const OpMaps* maps,
                                            const double* __restrict__ Jg, const double* __restrict__ ug,
                                            long long chunk, long long E, bool tma_ok, int lane) {
   using L = GradLayout;
   const long long e0 = chunk * kCH;
-  if constexpr (TMA) {
-    if (tma_ok) {
-      if (elect_one()) {
-        fence_proxy_async();
-        mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
-        tma_load_2d(s, &maps->in, 0, (int)(chunk * (kCH / 2)), bar);               // u[16 el][35]
-        tma_load_2d(s + L::U_SLAB, &maps->jac, (int)e0, 0, bar);                   // J[9][16 el]
-      }
-    } else {
-      const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
-      for (int k = lane; k < L::U_SLAB; k += 32) s[k] = (k < ne * 35) ? ug[e0 * 35 + k] : 0.0;
-      for (int k = lane; k < 9 * kCH; k += 32) {
-        const int xr = k / kCH, el = k - xr * kCH;
-        s[L::U_SLAB + k] = (el < ne) ? Jg[(long long)xr * E + e0 + el] : 0.0;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar);
+  if (tma_ok) {
+    if (elect_one()) {
+      fence_proxy_async();
+      mbar_arrive_expect_tx(bar, L::SLOT_BYTES);
+      tma_load_2d(s, &maps->in, 0, (int)(chunk * (kCH / 2)), bar);               // u[16 el][35]
+      tma_load_2d(s + L::U_SLAB, &maps->jac, (int)e0, 0, bar);                   // J[9][16 el]
     }
   } else {
-    grad_issue_plain(s, bar, Jg, ug, e0, E, lane);
+    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+    for (int k = lane; k < L::U_SLAB; k += 32) s[k] = (k < ne * 35) ? ug[e0 * 35 + k] : 0.0;
+    for (int k = lane; k < 9 * kCH; k += 32) {
+      const int xr = k / kCH, el = k - xr * kCH;
+      s[L::U_SLAB + k] = (el < ne) ? Jg[(long long)xr * E + e0 + el] : 0.0;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
   }
 }
 
 // one group of NTG column tiles (starting at tile T0): DMMAs, then J applied to the
 // NTG*2/3 complete (dof, r)-triples this lane now holds, results staged in shared memory
-template <int T0, int NTG>
+// BULK (TMA = false instantiation): the x-slabs of the stage are OUT_BLOCK + 2 apart and slab x holds its data from
+// so[x] on -- 1 where the slab's run in global memory starts 8 (mod 16), so that the bulk store (which skips the first
+// and the last double then) finds a 16-byte aligned source
+template <int T0, int NTG, bool BULK = false>
 __device__ __forceinline__ void grad_group(const double* __restrict__ sB, const double (&a)[kME][GradLayout::KT],
-                                           const double (&Jr)[kME][9], double* stage, int g, int t, int lane) {
+                                           const double (&Jr)[kME][9], double* stage, int g, int t, int lane,
+                                           const int* so = nullptr) {
   using L = GradLayout;
   double acc[kME][NTG][2];
 #pragma unroll
@@ -849,8 +813,11 @@ __device__ __forceinline__ void grad_group(const double* __restrict__ sB, const 
       const double T2v = acc[m][(3 * q + 2) >> 1][(3 * q + 2) & 1];
       if (V0 / 3 + q < 8 || t < 3) {          // dof 9t + 8 exists only for t < 3
 #pragma unroll
-        for (int x = 0; x < 3; ++x)
-          o[x * OUT_BLOCK + q] = fma(Jr[m][3 * x + 2], T2v, fma(Jr[m][3 * x + 1], T1v, Jr[m][3 * x] * T0v));
+        for (int x = 0; x < 3; ++x) {
+          const double v = fma(Jr[m][3 * x + 2], T2v, fma(Jr[m][3 * x + 1], T1v, Jr[m][3 * x] * T0v));
+          if constexpr (BULK) o[x * (OUT_BLOCK + 2) + so[x] + q] = v;
+          else                o[x * OUT_BLOCK + q] = v;
+        }
       }
     }
   }
@@ -869,23 +836,30 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sB = reinterpret_cast<double*>(smem_raw);
   double* slots = sB + L::B_DOUBLES;
-  double* stages = slots + (size_t)NW * L::SLOT_DOUBLES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * 3 * OUT_BLOCK);
+  constexpr int PAD = TMA ? 0 : 2;                                  // bulk producer / stores: headroom per slab
+  constexpr int SLOT = L::SLOT_DOUBLES + PAD, SPITCH = OUT_BLOCK + PAD;
+  double* stages = slots + (size_t)NW * SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * 3 * SPITCH);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
-    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], TMA ? 1 : 32);   // plain producer: every lane arrives
+    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], TMA ? 1 : 33);   // bulk producer: 32 lanes + the elected one
     *work_ctr = 0u;
     mbar_fence_init();
   }
   __syncthreads();
   FNSM_TL_VAL(0, tl_entry_);
 
-  double* s = slots + (size_t)warp * L::SLOT_DOUBLES;
-  double* stage = stages + (size_t)warp * 3 * OUT_BLOCK;      // [x][16][35]
+  double* s = slots + (size_t)warp * SLOT;
+  double* stage = stages + (size_t)warp * 3 * SPITCH;         // [x][16][35]
   uint64_t* bar = &bars[warp];
-  const double* sJ = s + L::U_SLAB;
+  const double* sJ = s + L::U_SLAB + PAD;
+  // bulk instantiation: u sits at s + shu; slab x of the stage holds its data from so[x] on (see grad_group)
+  const int shu = TMA ? 0 : odd8(ug);
+  int so[3];
+#pragma unroll
+  for (int x = 0; x < 3; ++x) so[x] = TMA ? 0 : odd8(outg + (long long)x * E * 35);
   const long long nchunks = (E + kCH - 1) / kCH;
   const WorkQueue wq{work_ctr, nchunks};
   const int g = lane >> 2, t = lane & 3, tpad = t < 3 ? t : 2;
@@ -898,7 +872,10 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
   // fast start: raw D goes into the (still unused) output stages, ahead of the first work-item loads
   static_assert((size_t)NW * 3 * OUT_BLOCK >= 3 * 35 * 35, "raw operator does not fit the stage area");
   if constexpr (FS) stage_operator_raw<3 * 35 * 35, NW * 32>(stages, Dg);
-  if (cur < nchunks && !dbg_noload) grad_issue<TMA>(s, bar, &maps, Jg, ug, cur, E, tma, lane);
+  if (cur < nchunks && !dbg_noload) {
+    if constexpr (TMA) grad_issue(s, bar, &maps, Jg, ug, cur, E, tma, lane);
+    else               grad_issue_bulk(s, bar, Jg, ug, cur, nchunks, E, lane, shu);
+  }
   if constexpr (FS) {
     // sB[(tile*KT + kt)*32 + lane]: B[k = t][n = c], c = lane>>2 -> value v = 2*tile + (c&1) of lane c>>1
     stage_operator_raw_wait();
@@ -948,48 +925,55 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
       const int el = chunk_el(g, m);
 #pragma unroll
       for (int kt = 0; kt < L::KT; ++kt)       // k-slot j = 35 is padding (zero operator entries): reads j = 34
-        a[m][kt] = s[el * 35 + (kt == 8 ? 32 + tpad : 4 * kt + t)];
+        a[m][kt] = s[shu + el * 35 + (kt == 8 ? 32 + tpad : 4 * kt + t)];
 #pragma unroll
       for (int xr = 0; xr < 9; ++xr) Jr[m][xr] = sJ[xr * kCH + el];
     }
     __syncwarp();
     if (FS) nxt = wq.resolve(tk);
-    GradPlainCtx pc;
-    if constexpr (TMA) {
-      if (nxt < nchunks && !dbg_noload) grad_issue<TMA>(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
-    } else {
-      const long long e0n = nxt * kCH;
-      pc.active = nxt < nchunks;
-      pc.ne = (int)((E - e0n < kCH) ? (E - e0n) : kCH);
-      pc.nvalid = pc.ne * 35;
-      pc.lane = lane;
-      pc.s = smem_u32(s + lane);
-      pc.E2 = 2 * E;
-      pc.u = ug + e0n * 35 + lane;
-      pc.j = Jg + (long long)(lane >> 4) * E + e0n + (lane & (kCH - 1));
+    if (nxt < nchunks && !dbg_noload) {
+      if constexpr (TMA) grad_issue(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
+      else               grad_issue_bulk(s, bar, Jg, ug, nxt, nchunks, E, lane, shu);
     }
     if (!FS) tk = wq.ticket(lane);
 
     const long long e0 = cur * kCH;
-    grad_group<0, 3>(sB, a, Jr, stage, g, t, lane);
-    if constexpr (!TMA) grad_plain_step<0>(pc);
-    grad_group<3, 3>(sB, a, Jr, stage, g, t, lane);
-    if constexpr (!TMA) grad_plain_step<1>(pc);
-    grad_group<6, 3>(sB, a, Jr, stage, g, t, lane);
-    if constexpr (!TMA) grad_plain_step<2>(pc);
-    grad_group<9, 3>(sB, a, Jr, stage, g, t, lane);
-    if constexpr (!TMA) grad_plain_step<3>(pc);
-    grad_group<12, 2>(sB, a, Jr, stage, g, t, lane);
-    if constexpr (!TMA) { grad_plain_step<4>(pc); if (pc.active) cp_async_arrive_noinc(bar); }
+    grad_group<0, 3, !TMA>(sB, a, Jr, stage, g, t, lane, so);
+    grad_group<3, 3, !TMA>(sB, a, Jr, stage, g, t, lane, so);
+    grad_group<6, 3, !TMA>(sB, a, Jr, stage, g, t, lane, so);
+    grad_group<9, 3, !TMA>(sB, a, Jr, stage, g, t, lane, so);
+    grad_group<12, 2, !TMA>(sB, a, Jr, stage, g, t, lane, so);
     fence_proxy_async();
     __syncwarp();
     if (!dbg_nostore) {
-      if (tma) {
-        if (lane == 0) { tma_store_3d(&maps.out, stage, 0, (int)(cur * (kCH / 2)), 0); tma_store_commit(); }
+      if constexpr (TMA) {
+        if (tma) {
+          if (lane == 0) { tma_store_3d(&maps.out, stage, 0, (int)(cur * (kCH / 2)), 0); tma_store_commit(); }
+        } else {
+#pragma unroll
+          for (int x = 0; x < 3; ++x)
+            flush_plain(outg + ((long long)x * E + e0) * 35, stage + x * OUT_BLOCK, e0, E, lane);
+        }
+      } else if (cur + 1 < nchunks) {
+        // whole chunk: one bulk store per x-slab; a run that starts 8 (mod 16) leaves without its first and last
+        // double, which two lanes store directly
+        if (lane == 0) {
+#pragma unroll
+          for (int x = 0; x < 3; ++x)
+            bulk_store(outg + ((long long)x * E + e0) * 35 + so[x], stage + x * SPITCH + 2 * so[x], OUT_BLOCK * 8 - 16 * so[x]);
+          tma_store_commit();
+        }
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+          if (so[x] && lane >= 1 && lane < 3) {
+            const int k = lane == 1 ? 0 : OUT_BLOCK - 1;
+            outg[((long long)x * E + e0) * 35 + k] = stage[x * SPITCH + 1 + k];
+          }
+        }
       } else {
 #pragma unroll
         for (int x = 0; x < 3; ++x)
-          flush_plain(outg + ((long long)x * E + e0) * 35, stage + x * OUT_BLOCK, e0, E, lane);
+          flush_plain(outg + ((long long)x * E + e0) * 35, stage + x * SPITCH + so[x], e0, E, lane);
       }
     }
     if (n == 0) FNSM_TL(4);
@@ -1016,64 +1000,56 @@ struct LiftLayout {
   static constexpr uint32_t SLOT_BYTES = SLOT_DOUBLES * 8;
 };
 
+// bulk producer of a lift item (see div_issue_bulk): the four face slabs (16 x 15 doubles each) as 1-D bulk copies
+// into regions with two doubles of headroom (slab f at s + f (V_SLAB + 2) + ((shm >> f) & 1)), the 4 x 16 face
+// Jacobians by 8-byte cp.async from every lane, 33 arrivals
+__device__ __forceinline__ int lift_shift_mask(const double* vg, long long E) {
+  int m = 0;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) m |= odd8(vg + (long long)f * E * 15) << f;
+  return m;
+}
 template <bool FE>
-__device__ __forceinline__ void lift_issue_plain(double* s, uint64_t* bar, const double* __restrict__ Jg,
-                                              const double* __restrict__ vg, long long e0, long long E, int lane) {
+__device__ __forceinline__ void lift_issue_bulk(double* s, uint64_t* bar, const double* __restrict__ Jg,
+                                                const double* __restrict__ vg, long long chunk, long long nchunks,
+                                                long long E, int lane, int shm) {
   using L = LiftLayout;
-    const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+  constexpr int P = L::V_SLAB + 2;
+  const long long e0 = chunk * kCH;
+  const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+  if (chunk + 1 < nchunks) {
+    if (elect_one()) {
+      fence_proxy_async();
+      mbar_arrive_expect_tx(bar, 4 * L::V_SLAB * 8 + 16 * __popc(shm));
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const int sh = (shm >> f) & 1;
+        bulk_load(s + f * P, vg + ((long long)f * E + e0) * 15 - sh, L::V_SLAB * 8 + 16 * sh, bar);
+      }
+    }
+  } else {                                   // last chunk: element-wise (partial; end of the arrays)
 #pragma unroll
     for (int f = 0; f < 4; ++f)
-      cp_async_run<L::V_SLAB>(s + f * L::V_SLAB, vg + ((long long)f * E + e0) * 15, ne * 15, lane);
+      cp_async_run<L::V_SLAB>(s + f * P + ((shm >> f) & 1), vg + ((long long)f * E + e0) * 15, ne * 15, lane);
+    if (elect_one()) mbar_arrive(bar);
+  }
 #pragma unroll
-    for (int q = 0; q < (4 * kCH) / 32; ++q) {
-      const int k = lane + 32 * q;
-      if (FE) { const int f = k / kCH, el = k - f * kCH; if (el < ne) cp_async8(s + 4 * L::V_SLAB + k, Jg + (long long)f * E + e0 + el); }
-      else    { const int el = k / 4; if (el < ne) cp_async8(s + 4 * L::V_SLAB + k, Jg + e0 * 4 + k); }
-    }
-    cp_async_arrive_noinc(bar);
+  for (int q = 0; q < (4 * kCH) / 32; ++q) {
+    const int k = lane + 32 * q;
+    if (FE) { const int f = k / kCH, el = k - f * kCH; if (el < ne) cp_async8(s + 4 * P + k, Jg + (long long)f * E + e0 + el); }
+    else    { const int el = k / 4; if (el < ne) cp_async8(s + 4 * P + k, Jg + e0 * 4 + k); }
+  }
+  cp_async_arrive_noinc(bar);
 }
 
-// plain producer of a lift item spread over its 15 k-tiles (see DivPlainCtx): 8 rows of 32 doubles per face slab
-// (the last one half full) = 32 copies + 2 for the face Jacobians
-struct LiftPlainCtx {
-  uint32_t s;
-  const double* v[4];         // face slab f of the next item + lane
-  const double* j;            // FE: row (lane >> 4), element e0 + (lane & 15); EF: e0 * 4 + lane
-  long long E2;
-  int nvalid, ne, lane;
-  bool active;
-};
-template <bool FE, int KTI>
-__device__ __forceinline__ void lift_plain_step(const LiftPlainCtx& c) {
-  using L = LiftLayout;
-  constexpr int ROWS = (L::V_SLAB + 31) / 32, NV = 4 * ROWS;    // 8, 32
-  constexpr int PER = (NV + L::KT - 1) / L::KT;                 // 3 (k-tiles 0..10 carry the slabs)
-  if (!c.active) return;
-#pragma unroll
-  for (int h = 0; h < PER; ++h) {
-    const int ci = KTI * PER + h;                               // constant after unrolling
-    if (ci < NV) {
-      const int f = ci / ROWS, q = ci % ROWS;
-      if (c.lane + 32 * q < c.nvalid)
-        cp_async8_rr(c.s + (f * L::V_SLAB + 32 * q) * 8, c.v[f] + 32 * q);
-    }
-  }
-  if constexpr (KTI >= L::KT - 2) {                             // Jacobians on the last two k-tiles
-    constexpr int q = KTI - (L::KT - 2);
-    const int k = c.lane + 32 * q;
-    if (FE) { if ((c.lane & (kCH - 1)) < c.ne) cp_async8_rr(c.s + (4 * L::V_SLAB + 32 * q) * 8, c.j + (long long)q * c.E2); }
-    else    { if ((k >> 2) < c.ne) cp_async8_rr(c.s + (4 * L::V_SLAB + 32 * q) * 8, c.j + 32 * q); }
-  }
-}
-
-template <bool FE, bool TMA>
+template <bool FE>
 __device__ __forceinline__ void lift_issue(double* s, uint64_t* bar, const CUtensorMap* map_v,
                                            const CUtensorMap* map_j, const double* __restrict__ Jg,
                                            const double* __restrict__ vg, long long chunk, long long E,
                                            bool tma_ok, int lane) {
   using L = LiftLayout;
   const long long e0 = chunk * kCH;
-  if constexpr (TMA) {
+  {
     if (tma_ok) {
       if (elect_one()) {
         fence_proxy_async();
@@ -1096,8 +1072,6 @@ __device__ __forceinline__ void lift_issue(double* s, uint64_t* bar, const CUten
       __syncwarp();
       if (lane == 0) mbar_arrive(bar);
     }
-  } else {
-    lift_issue_plain<FE>(s, bar, Jg, vg, e0, E, lane);
   }
 }
 
@@ -1118,23 +1092,25 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
   double* sB = reinterpret_cast<double*>(smem_raw);
   double* sL = sB + L::B_MAIN;
   double* slots = sB + L::B_DOUBLES;
-  double* stages = slots + (size_t)NW * L::SLOT_DOUBLES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * OUT_BLOCK);
+  constexpr int PAD = TMA ? 0 : 2;                                  // bulk producer / stores: headroom per slab
+  constexpr int P = L::V_SLAB + PAD, SLOT = L::SLOT_DOUBLES + 4 * PAD, SPITCH = OUT_BLOCK + PAD;
+  double* stages = slots + (size_t)NW * SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)NW * SPITCH);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   unsigned* work_ctr = reinterpret_cast<unsigned*>(bars + NW);
   if (threadIdx.x == 0) {
-    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], TMA ? 1 : 32);   // plain producer: every lane arrives
+    for (int w = 0; w < NW; ++w) mbar_init(&bars[w], TMA ? 1 : 33);   // bulk producer: 32 lanes + the elected one
     *work_ctr = 0u;
     mbar_fence_init();
   }
   __syncthreads();
   FNSM_TL_VAL(0, tl_entry_);
 
-  double* s = slots + (size_t)warp * L::SLOT_DOUBLES;
-  double* stage = stages + (size_t)warp * OUT_BLOCK;
+  double* s = slots + (size_t)warp * SLOT;
+  double* stage = stages + (size_t)warp * SPITCH;
   uint64_t* bar = &bars[warp];
-  const double* sJ = s + 4 * L::V_SLAB;
+  const double* sJ = s + 4 * P;
   const long long nchunks = (E + kCH - 1) / kCH;
   // work unit of the queue: a chunk (the warp walks its fields), or with FS one item, id = chunk * nrows + field
   // (< 2^30: division by nrows <= 8 as a multiplication by ceil(2^32 / nrows), exact in that range)
@@ -1157,8 +1133,17 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
   // fast start: the raw operator goes into the (still unused) output stages, ahead of the first work-item loads
   static_assert((size_t)NW * OUT_BLOCK >= 35 * 4 * 15, "raw operator does not fit the stage area");
   if constexpr (FS) stage_operator_raw<35 * 4 * 15, NW * 32>(stages, Og);
-  if (cur < nchunks)
-    lift_issue<FE, TMA>(s, bar, &maps.in[fld], &maps.jac, Jg, static_cast<const double*>(rows.field[fld]), cur, E, tma, lane);
+  // bulk instantiation: shift bits of the four face slabs of the item in the slot (they depend on the field's base)
+  int shm = 0;
+  if (cur < nchunks) {
+    const double* vg = static_cast<const double*>(rows.field[fld]);
+    if constexpr (TMA) {
+      lift_issue<FE>(s, bar, &maps.in[fld], &maps.jac, Jg, vg, cur, E, tma, lane);
+    } else {
+      shm = lift_shift_mask(vg, E);
+      lift_issue_bulk<FE>(s, bar, Jg, vg, cur, nchunks, E, lane, shm);
+    }
+  }
   if constexpr (FS) {
     // sB[(kt*4 + nt)*32 + lane] = Op(f, 8nt+g, j),  k = 4kt+t = 15 f + j
     stage_operator_raw_wait();
@@ -1217,19 +1202,24 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
 #pragma unroll
       for (int f = 0; f < 4; ++f) Jf[f] = FE ? sJ[f * kCH + el] : sJ[el * 4 + f];
       const double* sv = s + el * 15 + t;
+      int sh4[4];                                // bulk instantiation: where face slab f starts inside its region
+#pragma unroll
+      for (int f = 0; f < 4; ++f) sh4[f] = TMA ? 0 : (shm >> f) & 1;
 #pragma unroll
       for (int kt = 0; kt < L::KT; ++kt) {
         // k = 4kt + t = 15 f + j: f = F0 for t < THR, F0 + 1 above (THR >= 4: the tile does not straddle a face)
         const int F0 = (4 * kt) / 15, THR = 15 * (F0 + 1) - 4 * kt;
         // address of v[f][el][j] = f*V_SLAB + el*15 + (k - 15 f) = el*15 + t + 4kt + (V_SLAB - 15) f
-        const int off0 = 4 * kt + (L::V_SLAB - 15) * F0;
+        const int off0 = 4 * kt + (P - 15) * F0;
         double jf = Jf[F0], v;
         if (THR < 4) {
           const bool up = t >= THR;
-          v = sv[off0 + (up ? (L::V_SLAB - 15) : 0)];
+          if constexpr (TMA) v = sv[off0 + (up ? (L::V_SLAB - 15) : 0)];
+          else               v = sv[off0 + (up ? (P - 15) + sh4[F0 + 1 < 4 ? F0 + 1 : 3] : sh4[F0])];
           jf = up ? Jf[F0 + 1 < 4 ? F0 + 1 : 3] : jf;
         } else {
-          v = sv[off0];
+          if constexpr (TMA) v = sv[off0];
+          else               v = sv[off0 + sh4[F0]];
         }
         a[m][kt] = jf * v;
       }
@@ -1250,22 +1240,15 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
       nfld = advance ? 0 : fld + 1;
       nchunk = advance ? nxt : cur;
     }
-    LiftPlainCtx pc;
-    if constexpr (TMA) {
-      if (nchunk < nchunks)
-        lift_issue<FE, TMA>(s, bar, &maps.in[nfld], &maps.jac, Jg, static_cast<const double*>(rows.field[nfld]), nchunk, E, tma, lane);
-    } else {                                       // plain producer: spread over the k-tiles below
-      const long long e0n = nchunk * kCH;
+    int shn = 0;
+    if (nchunk < nchunks) {
       const double* vg = static_cast<const double*>(rows.field[nfld]);
-      pc.active = nchunk < nchunks;
-      pc.ne = (int)((E - e0n < kCH) ? (E - e0n) : kCH);
-      pc.nvalid = pc.ne * 15;
-      pc.lane = lane;
-      pc.s = smem_u32(s + lane);
-      pc.E2 = 2 * E;
-#pragma unroll
-      for (int f = 0; f < 4; ++f) pc.v[f] = vg + ((long long)f * E + e0n) * 15 + lane;
-      pc.j = FE ? Jg + (long long)(lane >> 4) * E + e0n + (lane & (kCH - 1)) : Jg + e0n * 4 + lane;
+      if constexpr (TMA) {
+        lift_issue<FE>(s, bar, &maps.in[nfld], &maps.jac, Jg, vg, nchunk, E, tma, lane);
+      } else {
+        shn = lift_shift_mask(vg, E);
+        lift_issue_bulk<FE>(s, bar, Jg, vg, nchunk, nchunks, E, lane, shn);
+      }
     }
 
     if (!FS && advance) tk = wq.ticket(lane);      // ticket after next; its latency hides under the DMMAs
@@ -1279,57 +1262,36 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
 #pragma unroll
       for (int d = 0; d < kNL; ++d) { accL[0][m][d] = 0.0; accL[1][m][d] = 0.0; }
     }
-    if constexpr (TMA) {
+    {
 #pragma unroll
-      for (int kt = 0; kt < L::KT; ++kt) {
-        const double* bp = sB + (kt * kNT) * 32 + lane;
+    for (int kt = 0; kt < L::KT; ++kt) {
+      const double* bp = sB + (kt * kNT) * 32 + lane;
 #pragma unroll
-        for (int nt = 0; nt < kNT; ++nt) {
-          const double b = bp[nt * 32];
+      for (int nt = 0; nt < kNT; ++nt) {
+        const double b = bp[nt * 32];
 #pragma unroll
-          for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m][kt], b);
-        }
-        const double2 l01 = *reinterpret_cast<const double2*>(sL + (kt * 4 + t) * 4);
-        const double l2 = sL[(kt * 4 + t) * 4 + 2];
-#pragma unroll
-        for (int m = 0; m < kME; ++m) {
-          accL[kt & 1][m][0] = fma(a[m][kt], l01.x, accL[kt & 1][m][0]);
-          accL[kt & 1][m][1] = fma(a[m][kt], l01.y, accL[kt & 1][m][1]);
-          accL[kt & 1][m][2] = fma(a[m][kt], l2, accL[kt & 1][m][2]);
-        }
+        for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m][kt], b);
       }
-    } else {
-      auto ktile = [&](auto ktc) {
-        constexpr int kt = decltype(ktc)::value;
-        const double* bp = sB + (kt * kNT) * 32 + lane;
+      const double2 l01 = *reinterpret_cast<const double2*>(sL + (kt * 4 + t) * 4);
+      const double l2 = sL[(kt * 4 + t) * 4 + 2];
 #pragma unroll
-        for (int nt = 0; nt < kNT; ++nt) {
-          const double b = bp[nt * 32];
-#pragma unroll
-          for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m][kt], b);
-        }
-        const double2 l01 = *reinterpret_cast<const double2*>(sL + (kt * 4 + t) * 4);
-        const double l2 = sL[(kt * 4 + t) * 4 + 2];
-#pragma unroll
-        for (int m = 0; m < kME; ++m) {
-          accL[kt & 1][m][0] = fma(a[m][kt], l01.x, accL[kt & 1][m][0]);
-          accL[kt & 1][m][1] = fma(a[m][kt], l01.y, accL[kt & 1][m][1]);
-          accL[kt & 1][m][2] = fma(a[m][kt], l2, accL[kt & 1][m][2]);
-        }
-        lift_plain_step<FE, kt>(pc);
-      };
-      static_for<L::KT>(ktile);
-      if (pc.active) cp_async_arrive_noinc(bar);
+      for (int m = 0; m < kME; ++m) {
+        accL[kt & 1][m][0] = fma(a[m][kt], l01.x, accL[kt & 1][m][0]);
+        accL[kt & 1][m][1] = fma(a[m][kt], l01.y, accL[kt & 1][m][1]);
+        accL[kt & 1][m][2] = fma(a[m][kt], l2, accL[kt & 1][m][2]);
+      }
+    }
     }
 
     const long long c = cur;
     const long long e0 = c * kCH;
     double* outg = static_cast<double*>(rows.out[fld]);
+    const int so = TMA ? 0 : odd8(outg);           // bulk stores: the block is staged from stage + so on
     if (lane == 0) tma_store_wait_read();
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < kME; ++m) {
-      double* o = stage + chunk_el(g, m) * 35;
+      double* o = stage + so + chunk_el(g, m) * 35;
       const double l0 = quad_sum(accL[0][m][0] + accL[1][m][0]), l1 = quad_sum(accL[0][m][1] + accL[1][m][1]),
                    l2 = quad_sum(accL[0][m][2] + accL[1][m][2]);
 #pragma unroll
@@ -1341,16 +1303,32 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
     }
     fence_proxy_async();
     __syncwarp();
-    if (tma) {
-      if (lane == 0) { tma_store_2d(&maps.out[fld], stage, 0, (int)(c * (kCH / 2))); tma_store_commit(); }
+    if constexpr (TMA) {
+      if (tma) {
+        if (lane == 0) { tma_store_2d(&maps.out[fld], stage, 0, (int)(c * (kCH / 2))); tma_store_commit(); }
+      } else {
+        flush_plain(outg + e0 * 35, stage, e0, E, lane);
+      }
+    } else if (c + 1 < nchunks) {
+      // whole block: one bulk store; a run that starts 8 (mod 16) leaves without its first and last double, which
+      // two lanes store directly (see k_grad_dmma)
+      if (lane == 0) {
+        bulk_store(outg + e0 * 35 + so, stage + 2 * so, OUT_BLOCK * 8 - 16 * so);
+        tma_store_commit();
+      }
+      if (so && lane >= 1 && lane < 3) {
+        const int k = lane == 1 ? 0 : OUT_BLOCK - 1;
+        outg[e0 * 35 + k] = stage[1 + k];
+      }
     } else {
-      flush_plain(outg + e0 * 35, stage, e0, E, lane);
+      flush_plain(outg + e0 * 35, stage + so, e0, E, lane);
     }
     if (n == 0) FNSM_TL(4);
     FNSM_TL_VAL(7, n + 1);
     if (FS) cur = nchunk;
     else if (advance) { cur = nchunk; nxt = wq.resolve(tk); }
     fld = nfld;
+    shm = shn;
   }
   FNSM_TL(5);
   if (lane == 0) tma_store_wait_all();
@@ -1531,8 +1509,8 @@ static int launch_dmma_plain(int kind, const void* jac, const void* op, const Op
   if (kind == FNSM_OP_DIV || kind == FNSM_OP_GRAD) {
     const bool is_div = kind == FNSM_OP_DIV;
     const int NW = is_div ? 12 : 10;
-    const size_t smem = is_div ? 8 * ((size_t)DivLayout::B_DOUBLES + (size_t)NW * DivLayout::SLOT_DOUBLES) + 8 * (size_t)NW + 8
-                               : 8 * ((size_t)GradLayout::B_DOUBLES + (size_t)NW * (GradLayout::SLOT_DOUBLES + 3 * OUT_BLOCK)) + 8 * (size_t)NW + 8;
+    const size_t smem = is_div ? 8 * ((size_t)DivLayout::B_DOUBLES + (size_t)NW * DivLayout::SLOT_DOUBLES_BULK) + 8 * (size_t)NW + 8
+                               : 8 * ((size_t)GradLayout::B_DOUBLES + (size_t)NW * (GradLayout::SLOT_DOUBLES + 2 + 3 * (OUT_BLOCK + 2))) + 8 * (size_t)NW + 8;
     const bool fs = fast_start(kind, nchunks, di.sms, NW, fs_mode);
     auto go = [&](auto kernel, auto pdl) {
       if (int rc = set_smem(kernel, smem)) return rc;
@@ -1548,7 +1526,7 @@ static int launch_dmma_plain(int kind, const void* jac, const void* op, const Op
     return fs ? go(k_grad_dmma<10, false, true>, std::true_type{}) : go(k_grad_dmma<10, false, false>, std::false_type{});
   }
   constexpr int NW = 16;
-  const size_t smem = 8 * ((size_t)LiftLayout::B_DOUBLES + (size_t)NW * (LiftLayout::SLOT_DOUBLES + OUT_BLOCK)) + 8 * (size_t)NW + 8;
+  const size_t smem = 8 * ((size_t)LiftLayout::B_DOUBLES + (size_t)NW * (LiftLayout::SLOT_DOUBLES + 8 + OUT_BLOCK + 2)) + 8 * (size_t)NW + 8;
   LiftMaps lmaps{};
   const bool fs = fast_start(kind, nchunks, di.sms, NW, fs_mode);
   auto go = [&](auto kernel, auto pdl) {

@@ -138,6 +138,29 @@ __device__ __forceinline__ void grad2_compute(const double (&a)[kME][9], const d
   }
 }
 
+// plain (non-TMA) producer of this experiment: 8-byte cp.async from every lane, completing on the slot's barrier
+// (32 arrivals).  k_grad_dmma has since moved to 1-D bulk copies (grad_issue_bulk); this kernel keeps the first form.
+__device__ __forceinline__ void grad2_issue_plain(double* s, uint64_t* bar, const double* __restrict__ Jg,
+                                                  const double* __restrict__ ug, long long e0, long long E, int lane) {
+  using L = GradLayout;
+  const int ne = (int)((E - e0 < kCH) ? (E - e0) : kCH);
+  cp_async_run<L::U_SLAB>(s, ug + e0 * 35, ne * 35, lane);
+  const int el = lane & (kCH - 1);
+  const double* src = Jg + (long long)(lane >> 4) * E + e0 + el;
+#pragma unroll
+  for (int q = 0; q < (9 * kCH + 31) / 32; ++q)
+    if (lane + 32 * q < 9 * kCH && el < ne) cp_async8(s + L::U_SLAB + lane + 32 * q, src + (long long)(2 * q) * E);
+  cp_async_arrive_noinc(bar);
+}
+struct GradPlainCtx {
+  uint32_t s;
+  const double* u;            // next chunk + lane
+  const double* j;            // row (lane >> 4), element e0 + (lane & 15)
+  long long E2;
+  int nvalid, ne, lane;
+  bool active;
+};
+
 template <int NW, bool TMA = true>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_grad2_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, const double* __restrict__ Dg,
@@ -169,7 +192,10 @@ k_grad2_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg,
   const bool tma = TMA && (flags & kFlagTma);
 
   long long cur = wq.take(lane), nxt = wq.take(lane);
-  if (cur < nchunks) grad_issue<TMA>(s, bar, &maps, Jg, ug, cur, E, tma, lane);
+  if (cur < nchunks) {
+    if constexpr (TMA) grad_issue(s, bar, &maps, Jg, ug, cur, E, tma, lane);
+    else               grad2_issue_plain(s, bar, Jg, ug, cur * kCH, E, lane);
+  }
   stage_div_tables(sB, sL, Dg);
   __syncthreads();
   const uint32_t bB = smem_u32(sB) + lane * 16, bL = smem_u32(sL) + t * 32;
@@ -188,7 +214,7 @@ k_grad2_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg,
     __syncwarp();
     const long long e0 = cur * kCH;
     if constexpr (TMA) {
-      if (nxt < nchunks) grad_issue<TMA>(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
+      if (nxt < nchunks) grad_issue(s, bar, &maps, Jg, ug, nxt, E, tma, lane);
       const unsigned tk = wq.ticket(lane);
       grad2_compute(a, Jr, bB, bL, outg, e0, E, g, t, NoHook{});
       cur = nxt;

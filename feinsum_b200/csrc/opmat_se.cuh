@@ -211,7 +211,8 @@ static int launch_se_p4(const void* op, const SeRows& rows, int nrows, long long
   // with a third of the divergence's slot there is room for the output stage (one TMA store per chunk instead of
   // 18 streaming stores per lane): ptxas then fits the loop into 168 registers with 8 bytes of spills instead of 124
   constexpr bool STAGED = true;
-  const size_t smem = 8 * ((size_t)L::B_DOUBLES + (size_t)NW * (L::SLOT_DOUBLES + (STAGED ? OUT_BLOCK : 0))) + 8 * (size_t)NW + 8;
+  // (sized for the TMA = false instantiation, whose slots carry two doubles of headroom per slab)
+  const size_t smem = 8 * ((size_t)L::B_DOUBLES + (size_t)NW * (L::SLOT_DOUBLES_BULK + (STAGED ? OUT_BLOCK : 0))) + 8 * (size_t)NW + 8;
   if (smem > (size_t)di.max_smem_optin) return FNSM_E_BAD_CONFIG;
   auto kernel = k_div_dmma<NW, STAGED, 0, 1, ES, true>;
   auto kernel_plain = k_div_dmma<NW, STAGED, 0, 1, ES, false>;
