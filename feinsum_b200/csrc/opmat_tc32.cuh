@@ -120,11 +120,29 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ int shift16(const void* p) { return (int)(reinterpret_cast<uintptr_t>(p) & 15); }
-// nbytes (multiple of 4) from the 4-byte aligned global address g to s_base + shift16(g); s_base is 16-byte aligned
+// tx bytes added to the pending phase without an arrival (the arrivals are the threads' cp_async_arrive)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// nbytes (multiple of 4) from the 4-byte aligned global address g to s_base + shift16(g); s_base is 16-byte aligned.
+// `whole` (every tile but the last of the arrays): ONE 1-D bulk copy by thread 0 of the group, from g rounded down to
+// g + nbytes rounded up to 16 bytes -- the few bytes in front and behind belong to the neighbouring tiles / slabs --
+// with the bytes announced on `bar`, where every thread of the group still arrives (cp_async_arrive).  The cooperative
+// cp.async form below (~9 LDGSTS per thread and slab behind a rolled, branchy loop) is what the last tile takes: it
+// is partial, and rounding its end up would read past the arrays.
 template <int NT>
-__device__ __forceinline__ void plain_load_async(unsigned char* s_base, const void* gp, int nbytes, int tid) {
+__device__ __forceinline__ void plain_load_async(unsigned char* s_base, const void* gp, int nbytes, int tid,
+                                                 uint64_t* bar, bool whole) {
   const unsigned char* g = static_cast<const unsigned char*>(gp);
   const int a = shift16(g);
+  if (whole) {
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)(a + nbytes + 15) & ~15u;
+      mbar_expect_tx(bar, bytes);
+      bulk_load(s_base, g - a, bytes, bar);
+    }
+    return;
+  }
   const uint32_t s = smem_u32(s_base) + a;
   int head = (16 - a) & 15;
   if (head > nbytes) head = nbytes;
@@ -133,7 +151,9 @@ __device__ __forceinline__ void plain_load_async(unsigned char* s_base, const vo
   for (int o = head + 16 * tid; o < end; o += 16 * NT) cp_async16(s + o, g + o);
   if (tid < ((nbytes - end) >> 2)) cp_async4(s + end + 4 * tid, g + end + 4 * tid);
 }
-// the reverse: nbytes staged at s_base + shift16(g) -> global g (streaming 16-byte stores + ragged ends)
+// the reverse: nbytes staged at s_base + shift16(g) -> global g: the 16-byte aligned middle as one bulk store by
+// thread 0 (bulk async-group: tma_store_wait_read before the stage is rewritten), the ragged ends (< 16 bytes each)
+// by the first threads.  The caller has fenced (fence.proxy.async) and synchronised the group.
 template <int NT>
 __device__ __forceinline__ void plain_store(void* gp, const unsigned char* s_base, int nbytes, int tid) {
   unsigned char* g = static_cast<unsigned char*>(gp);
@@ -141,12 +161,19 @@ __device__ __forceinline__ void plain_store(void* gp, const unsigned char* s_bas
   const unsigned char* s = s_base + a;
   int head = (16 - a) & 15;
   if (head > nbytes) head = nbytes;
-  if (tid < (head >> 2)) *reinterpret_cast<float*>(g + 4 * tid) = *reinterpret_cast<const float*>(s + 4 * tid);
   const int body = (nbytes - head) & ~15, end = head + body;
-  for (int o = head + 16 * tid; o < end; o += 16 * NT)
-    stg_stream(reinterpret_cast<float4*>(g + o), *reinterpret_cast<const float4*>(s + o));
-  if (tid < ((nbytes - end) >> 2))
-    *reinterpret_cast<float*>(g + end + 4 * tid) = *reinterpret_cast<const float*>(s + end + 4 * tid);
+  if (tid == 0) {
+    if (body > 0) bulk_store(g + head, s + head, (uint32_t)body);
+    tma_store_commit();
+  }
+  if (tid >= 32 && tid < 32 + (head >> 2)) {
+    const int k = tid - 32;
+    *reinterpret_cast<float*>(g + 4 * k) = *reinterpret_cast<const float*>(s + 4 * k);
+  }
+  if (tid >= 64 && tid < 64 + ((nbytes - end) >> 2)) {
+    const int k = tid - 64;
+    *reinterpret_cast<float*>(g + end + 4 * k) = *reinterpret_cast<const float*>(s + end + 4 * k);
+  }
 }
 constexpr int kPlainPad = 128;      // slack per slab of a slot / stage in the non-TMA kernels (shift <= 12 B; keeps 128-B alignment)
 
@@ -266,7 +293,7 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
     } else {
       const long long e0 = tl * L::TM;
       const int rows = (int)(E - e0 < L::TM ? E - e0 : L::TM);
-      plain_load_async<L::GT>(slot_b[p], ug + e0 * ND, rows * ND * 4, gtid);
+      plain_load_async<L::GT>(slot_b[p], ug + e0 * ND, rows * ND * 4, gtid, &full[p], tl + 1 < ntiles);
       cp_async_arrive(&full[p]);
     }
   };
@@ -294,8 +321,8 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
     }
     mbar_wait(&full[s], (it >> 1) & 1u);
     // the A operand aliases the output stage: the previous tile's bulk store must have read it out
-    // (plain drain: every thread finished its share of the copy before it got here)
-    if (TMA && leader) tma_store_wait_read();
+    // (bulk drain: the leader waits for its bulk store of the previous tile to have read the stage out)
+    if (leader) tma_store_wait_read();
     group_barrier(bar_id, L::GT);
     // ---- element row -> A_hi / A_lo (K-major canonical layout: 16-byte k-quads, rows 16 B apart) ----
     {
@@ -373,7 +400,7 @@ k_grad_tc32(const __grid_constant__ GradTCMaps maps, const float* __restrict__ J
         plain_store<L::GT>(outg + ((long long)x * E + e0) * ND, stage_b + x * OUT_SLAB, rows * ND * 4, gtid);
     }
   }
-  if (TMA && leader) tma_store_wait_all();
+  if (leader) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(*tmem_slot, 512);
@@ -490,7 +517,8 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
       const float* vg = static_cast<const float*>(rows.field[fld]);
 #pragma unroll
       for (int f = 0; f < 4; ++f)
-        plain_load_async<L::GT>(slot_b[s] + f * V_SLAB_B, vg + ((long long)f * E + e0) * NFD, nr * NFD * 4, gtid);
+        plain_load_async<L::GT>(slot_b[s] + f * V_SLAB_B, vg + ((long long)f * E + e0) * NFD, nr * NFD * 4, gtid,
+                                &full[s], tl + 1 < ntiles);
       cp_async_arrive(&full[s]);
     }
   };
@@ -565,7 +593,7 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
       if (TMA && it + 2 < nitems) fence_proxy_async();
     }
     if (it + 2 < nitems) issue(it + 2, s);
-    if (TMA && leader) tma_store_wait_read();            // the stage is free again (previous item's store)
+    if (leader) tma_store_wait_read();            // the stage is free again (previous item's store)
     if (fld == 0) load_j(tile + tstride, Jn);            // next tile's face Jacobians, behind the last use of Jf (see k_div_tc32)
     mbar_wait(mma_done, (uint32_t)it & 1u);
     tc_fence_after();
@@ -597,7 +625,7 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
     }
     if (++fld == nrows) { fld = 0; tile += tstride; }
   }
-  if (TMA && leader) tma_store_wait_all();
+  if (leader) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(*tmem_slot, 512);
@@ -711,7 +739,8 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
       const int nr = (int)(E - e0 < L::TM ? E - e0 : L::TM);
 #pragma unroll
       for (int x = 0; x < 3; ++x)
-        plain_load_async<L::GT>(slot_b + x * U_SLAB_B, ug + ((long long)x * E + e0) * ND, nr * ND * 4, gtid);
+        plain_load_async<L::GT>(slot_b + x * U_SLAB_B, ug + ((long long)x * E + e0) * ND, nr * ND * 4, gtid,
+                                full, tl + 1 < ntiles);
       cp_async_arrive(full);
     }
   };
@@ -769,7 +798,7 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
       if (r == L::NCHUNK - 1) {
         // every thread is past its last read of the slot: fetch this group's next tile
         if (tile + tstride < ntiles) fetch(tile + tstride);
-        if (TMA && leader) tma_store_wait_read();        // the stage is free again (previous tile's store)
+        if (leader) tma_store_wait_read();        // the stage is free again (previous tile's store)
       }
     }
     {
@@ -808,7 +837,7 @@ k_div_tc32(const __grid_constant__ DivTCMaps maps, const float* __restrict__ Jg,
       plain_store<L::GT>(outg + e0 * ND, stage_b, (int)(E - e0 < L::TM ? E - e0 : L::TM) * ND * 4, gtid);
     }
   }
-  if (TMA && leader) tma_store_wait_all();
+  if (leader) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(*tmem_slot, 512);
