@@ -471,35 +471,31 @@ def test_lift_fast_start_row_counts(cq, b):
     check(E.lift_ef(b=b), 4243, cq, variant=1, fast_start=1)
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
 @pytest.mark.parametrize("n", [64, 5000, 100000])
-def test_dependent_launches_keep_stream_order(cq, n):
+def test_dependent_launches_keep_stream_order(cq, n, dtype):
     """lift -> grad -> lift ... back to back on one stream, each kernel consuming what the one before it wrote: the
-    fast-start kernels are launched with programmatic stream serialization and must not read before the previous
-    grid has completed."""
+    fast-start fp64 kernels and the tcgen05 fp32 kernels are launched with programmatic stream serialization and must
+    not read before the previous grid has completed."""
     import torch
 
-    lift, grad = E.lift_fe(b=1), E.grad()
+    lift, grad = E.lift_fe(b=1, dtype=dtype), E.grad(dtype=dtype)
     lin = np_oracle.generate_input_arrays(lift, n, 3)
     gin = np_oracle.generate_input_arrays(grad, n, 4)
     dev_l = {k: torch.from_numpy(v).to(cq.torch_device) for k, v in lin.items()}
     dev_g = {k: torch.from_numpy(v).to(cq.torch_device) for k, v in gin.items()}
-    ex_l = generate_cuda(lift).with_params(variant=1, fast_start=1).executor(cq)
-    ex_g = generate_cuda(grad).with_params(variant=1, fast_start=1).executor(cq)
-    lift_out = torch.zeros((n, 35), dtype=torch.float64, device=cq.torch_device)
-    grad_out = torch.zeros((3, n, 35), dtype=torch.float64, device=cq.torch_device)
-    ref_l = np_oracle.reference_outputs(lift, lin)["_fe_out"]
-    ref_g = np_oracle.reference_outputs(grad, {**gin, "u": ref_l})["_fe_out"]
+    params = dict(variant=1, fast_start=1) if dtype == "float64" else {}
+    ex_l = generate_cuda(lift).with_params(**params).executor(cq)
+    ex_g = generate_cuda(grad).with_params(**params).executor(cq)
+    tdt = getattr(torch, dtype)
+    lift_out = torch.zeros((n, 35), dtype=tdt, device=cq.torch_device)
+    grad_out = torch.zeros((3, n, 35), dtype=tdt, device=cq.torch_device)
+    ref = np_oracle.reference_outputs if dtype == "float64" else np_oracle.reference_outputs_fp64
+    ref_l = ref(lift, lin)["_fe_out"]
+    ref_g = ref(grad, {**gin, "u": ref_l.astype(dtype)})["_fe_out"]
     for rep in range(20):
         lift_out.zero_()            # a foreign kernel ahead of the chain
         ex_l(cq, **dev_l, _fe_out=lift_out)
         evt, _ = ex_g(cq, **{**dev_g, "u": lift_out}, _fe_out=grad_out)
         evt.wait()
         np_oracle.assert_matches({"_fe_out": grad_out.cpu().numpy()}, {"_fe_out": ref_g}, north_star=True)
-
-
-@pytest.mark.parametrize("i", [1, 9, 30, 48])
-def test_tccg_contractions_run_on_the_generic_kernel(cq, i):
-    # reference utils.get_tccg_benchmark (src/feinsum/utils.py:206-233): fixed-size two-operand contractions
-    e = f.utils.get_tccg_benchmark(i)
-    assert generate_cuda(e).plan.kernel_id == "generic"
-    check(e, 1, cq, seed=i)
