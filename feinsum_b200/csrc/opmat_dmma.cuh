@@ -32,8 +32,9 @@
 //   * elements are permuted inside a chunk (el = 4*(g&3) + (g>>2) + 2m) so the
 //     stride-35 / stride-15 rows read by a half-warp fall into distinct banks.
 //
-// Unaligned inputs (odd E, misaligned base) take the plain producer: 8-byte cp.async by the lanes of the owning
-// warp, completing on the same mbarrier, results through coalesced stores from the stage.
+// Unaligned inputs (odd E, misaligned base) take the TMA = false instantiations: 1-D bulk copies (cp.async.bulk) of
+// whole slabs, shifted by one double where a slab starts 8 (mod 16), completing on the same mbarrier; results leave
+// through bulk stores from the stage (div_issue_bulk).  Small launches take the FS = true instantiations (k_div_dmma).
 #pragma once
 #include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through cudart)
 #include <utility>
