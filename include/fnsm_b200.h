@@ -19,6 +19,10 @@
  *     bound to E (reference measure.py:91-97, 226-233).  No allocation and no
  *     synchronisation happens inside; launches are asynchronous on `stream`
  *     (a cudaStream_t passed as void*), like the reference's in-order queue.
+ *     Small launches of the fp64 tensor kernels carry the programmatic-stream-
+ *     serialization attribute and execute griddepcontrol.wait before their first
+ *     global access: every read and write keeps stream order, only launch latency
+ *     and on-chip set-up overlap the previous kernel's tail.
  *   - return value: 0 on success, a positive cudaError_t, or a negative
  *     FNSM_E_* code.  fnsm_b200_strerror() decodes all three.
  *   - thread safety: concurrent calls on distinct streams are safe.  Global
@@ -77,7 +81,12 @@ typedef struct fnsm_cfg {
   int32_t threads;        /* threads per CTA                                         */
   int32_t stages;         /* depth of the global->shared pipeline                    */
   int32_t ctas_per_sm;    /* persistent grid = ctas_per_sm * #SM (0 = kernel default)*/
-  int32_t reserved[3];
+  int32_t reserved[3];    /* 0 = defaults.  Measurement / test switches of the fp64 tensor kernels, not tunables:
+                           * [0] bit 0 force the non-TMA (bulk-copy) producer, bits 1-2 skip loads / stores (timing
+                           * only, results invalid), bit 3 direct stores; [1] start-up phase offset between the
+                           * warps of a sub-partition (cycles); [2] bits 0-3 phase-ablation build of the divergence
+                           * kernel (results invalid), bits 4-5: 1 / 2 force the small-launch ("fast start")
+                           * instantiations on / off instead of choosing by the number of work items per warp */
 } fnsm_cfg;
 
 /* one integer tunable and its legal range, for fnsm_b200_query_cfg_space */
