@@ -126,8 +126,8 @@ def test_opmat_fp32_orders_without_tensor_kernel(cq):
 @pytest.mark.parametrize("builder", [E.grad, E.div, E.lift_ef, E.lift_fe])
 def test_opmat_fp32_tcgen05_plain_producer(cq, n, builder, variant):
     """n % 4 != 0: rows are not 16-byte multiples, no tensor map can describe the operands.  Round 1 fell back to
-    the mma.sync kernels here (63-77 % of roofline); now the tcgen05 kernels themselves run with a cp.async producer
-    and plain vector stores (TMA = false instantiation), for auto and for an explicit variant 3 alike.  Sizes cover
+    the mma.sync kernels here (63-77 % of roofline); now the tcgen05 kernels themselves run with a bulk-copy producer
+    and bulk stores (TMA = false instantiation), for auto and for an explicit variant 3 alike.  Sizes cover
     a single ragged tile, tile boundaries +-1, two full rounds of tiles + 5 and several tiles per group."""
     check(builder(dtype="float32"), n, cq, variant=variant)
 
@@ -168,17 +168,19 @@ def test_fp32_tensor_path_accuracy_margin(cq, variant):
             assert rel < 3e-6, (builder.__name__, k, rel)
 
 
+@pytest.mark.parametrize("n", [16, 1000, 1024, 2049])
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 @pytest.mark.parametrize("builder", [E.grad, E.div, E.lift_fe, E.lift_ef])
-def test_misaligned_operands_take_the_plain_path(cq, builder, dtype):
-    """Operands that are views at an odd offset into a larger allocation (bases not 16-byte aligned)
-    rule out every TMA tensor map: auto takes the plain producers (fp64: DMMA kernels with plain loads; fp32:
-    tcgen05 kernels with cp.async loads and vector stores, slabs shifted by the misalignment) and still matches
-    the oracle; outputs are views at an odd offset as well."""
+def test_misaligned_operands_take_the_plain_path(cq, builder, dtype, n):
+    """Operands that are views at an odd offset into a larger allocation (bases not 16-byte aligned) rule out every
+    TMA tensor map: auto takes the TMA = false instantiations (1-D bulk copies started at the address rounded down to
+    16 bytes, slabs shifted by the misalignment in shared memory; bulk stores of the aligned middle of a block + its
+    ragged ends) and still matches the oracle; outputs are views at an odd offset as well, and nothing outside them
+    is written.  Sizes: one chunk / tile, a ragged tail, whole chunks up to the end of the arrays (the last chunk must
+    not be read past its end), one element more than that."""
     import torch
 
     e = builder(dtype=dtype)
-    n = 1000
     ins = np_oracle.generate_input_arrays(e, n, 11)
     tdt = torch.float64 if dtype == "float64" else torch.float32
     dev = {}
@@ -190,14 +192,19 @@ def test_misaligned_operands_take_the_plain_path(cq, builder, dtype):
         assert view.data_ptr() % 16 != 0 and view.is_contiguous()
         dev[k] = view
     out_shape = tuple(int(d) if isinstance(d, (int, np.integer)) else n for d in e.shape)
+    flats = {}
     for name in e.output_names:
-        flat = torch.zeros(int(np.prod(out_shape)) + 3, dtype=tdt, device=cq.torch_device)
+        flat = torch.full((int(np.prod(out_shape)) + 8,), -7.0, dtype=tdt, device=cq.torch_device)
+        flats[name] = flat
         dev[name] = flat[1:1 + int(np.prod(out_shape))].view(out_shape)
     evt, outs = generate_cuda(e).executor(cq)(cq, **dev)
     evt.wait()
     got = {k: v.cpu().numpy() for k, v in outs.items()}
     ref = (np_oracle.reference_outputs_fp64 if dtype == "float32" else np_oracle.reference_outputs)(e, ins)
     np_oracle.assert_matches(got, ref, north_star=True)
+    for name, flat in flats.items():                       # canaries around the output views
+        host = flat.cpu().numpy()
+        assert host[0] == -7.0 and np.all(host[1 + int(np.prod(out_shape)):] == -7.0), name
 
 
 @pytest.mark.parametrize("n", [1, 100])
