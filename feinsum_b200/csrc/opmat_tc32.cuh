@@ -503,9 +503,14 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
   const long long nitems = my_tiles * nrows;
 
   // TMA: the leader; plain: every thread of the group moves its share of the four face slabs
-  auto issue = [&](long long item, int s) {
-    const long long tl = tile0 + (item / nrows) * tstride;
-    const int fld = (int)(item % nrows);
+  // items are issued in order, so the (tile, field) of the next one to issue advance by counting (a 64-bit division
+  // per item and thread is a visible share of a p = 1 tile)
+  long long issue_tl = tile0;
+  int issue_fld = 0;
+  auto issue = [&](int s) {
+    const long long tl = issue_tl;
+    const int fld = issue_fld;
+    if (++issue_fld == nrows) { issue_fld = 0; issue_tl += tstride; }
     if constexpr (TMA) {
       if (leader) {
         mbar_arrive_expect_tx(&full[s], L::SLOT_BYTES);
@@ -522,8 +527,8 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
       cp_async_arrive(&full[s]);
     }
   };
-  if (nitems > 0) issue(0, 0);
-  if (nitems > 1) issue(1, 1);
+  if (nitems > 0) issue(0);
+  if (nitems > 1) issue(1);
   const bool j_vec = TMA || shift16(Jg) == 0;            // J(E,4) rows are 16 bytes: vector load iff the base is aligned
   auto load_j = [&](long long tl, float (&J)[4]) {
     const long long e = tl * L::TM + row;
@@ -592,7 +597,7 @@ k_lift_tc32(const __grid_constant__ LiftTCMaps maps, const float* __restrict__ J
       umma_commit(mma_done);
       if (TMA && it + 2 < nitems) fence_proxy_async();
     }
-    if (it + 2 < nitems) issue(it + 2, s);
+    if (it + 2 < nitems) issue(s);
     if (leader) tma_store_wait_read();            // the stage is free again (previous item's store)
     if (fld == 0) load_j(tile + tstride, Jn);            // next tile's face Jacobians, behind the last use of Jf (see k_div_tc32)
     mbar_wait(mma_done, (uint32_t)it & 1u);
