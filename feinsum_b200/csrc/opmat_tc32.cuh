@@ -192,7 +192,7 @@ struct GradTC {
   static constexpr int NB = NP + N;                     // rows of the operator table: [hi | pad | lo] = 240
   // groups per CTA: the tiles of the lower orders are small (6-40 KB), so their fixed latencies (TMA, MMA
   // completion, group barriers) are covered by four independent groups instead of two
-  static constexpr int GROUPS = ND <= 4 ? 8 : (ND <= 20 ? 4 : 2);
+  static constexpr int GROUPS = ND <= 10 ? 8 : (ND <= 20 ? 4 : 2);
   static constexpr int WPG = GROUPS == 2 ? 8 : 4, GT = 32 * WPG, NH = WPG / 4;   // warps / threads per group, threads per row
   static constexpr int THREADS = GROUPS * GT;
   static constexpr int B_LBO = NB * 16;                 // operator table: addr(n, k) = (k/4) B_LBO + 16 n + 4 (k%4)
@@ -648,7 +648,7 @@ struct DivTC {
   static constexpr int KC = tc_pad(ND, 8), KS_C = KC / 8, NCHUNK = 3;   // per chunk: padded length (40), k-steps
   static constexpr int N = tc_pad(ND, 16), NB = 2 * N;  // 48; operator table rows [hi | lo] = 96
   static constexpr int WPG = 4, GT = 32 * WPG, NH = WPG / 4;
-  static constexpr int GROUPS = ND <= 4 ? 8 : (ND <= 10 ? 4 : (ND <= 20 ? 3 : 2)), THREADS = GROUPS * GT;   // see GradTC
+  static constexpr int GROUPS = ND <= 4 ? 8 : (ND <= 10 ? 5 : (ND <= 20 ? 3 : 2)), THREADS = GROUPS * GT;   // see GradTC
   static constexpr int B_LBO = NB * 16;                 // 1536
   static constexpr int B_BYTES = NCHUNK * (KC / 4) * B_LBO;   // 46 080
   static constexpr int U_SLAB = TM * ND;                // floats per x
@@ -656,7 +656,7 @@ struct DivTC {
   static constexpr int STAGE_BYTES = TM * ND * 4;       // 17 920
   static constexpr int NQ = (ND + 7) / 8;
   static constexpr int GROUP_BYTES = SLOT_BYTES + STAGE_BYTES;
-  static constexpr int TMEM_COLS_PER_GROUP = GROUPS == 2 ? 256 : (GROUPS == 3 ? 160 : (GROUPS == 4 ? 128 : 64));
+  static constexpr int TMEM_COLS_PER_GROUP = GROUPS == 2 ? 256 : (GROUPS == 3 ? 160 : (GROUPS == 4 ? 128 : (GROUPS == 5 ? 96 : 64)));
   static constexpr int A_COL = NB, A_BUF = 2 * KC, A_LO = KC;
   static_assert(A_COL + 2 * A_BUF <= TMEM_COLS_PER_GROUP, "TMEM budget");
   static_assert(SLOT_BYTES % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA alignment");
