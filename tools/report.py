@@ -31,6 +31,9 @@ def main() -> None:
     cq = f.CudaQueue(0)
     fp64 = max(_cabi.measure_peak(0), _cabi.measure_peak(3))
     fp32 = _cabi.measure_peak(1)
+    # the same micro-kernels after ~0.7 s of load: the board sits at its power cap, which is where timeit's >= 0.5 s
+    # loops run (the burst figure stays the denominator of the "% of roofline" column)
+    sus = {"float64": min(fp64, max(_cabi.measure_peak(16), _cabi.measure_peak(19))), "float32": min(fp32, _cabi.measure_peak(17))}
     device_info.register_measured_peaks(cq.device.name, float64=fp64, float32=fp32)
     bw = device_info.DEV_TO_PEAK_BW[cq.device.name]
     measure.N_MIN_SIM_SECS = args.secs
@@ -38,8 +41,9 @@ def main() -> None:
           f"HBM {bw:.1f} GB/s (MEASURED_PEAKS.json)\n")
     print("`feinsum_b200.measure.timeit` (validation gate, 5 warm-ups, CUDA events); FLOPs = flop-optimal contraction "
           "path, bytes = every operand and output once.\n")
-    print("| einsum | dtype | E | ms | GFLOP/s | GB/s | roofline GFLOP/s | % of roofline |")
-    print("|---|---|---|---|---|---|---|---|")
+    print(f"Sustained FP peaks (after 0.7 s of load): FP64 {sus['float64']:.0f}, FP32 {sus['float32']:.0f} GFLOP/s -> last column.\n")
+    print("| einsum | dtype | E | ms | GFLOP/s | GB/s | roofline GFLOP/s | % of roofline | % of the roofline at the sustained FP peak |")
+    print("|---|---|---|---|---|---|---|---|---|")
     cases = [("grad xre,rij,ej->xei", E.grad), ("div xre,rij,xej->ei", E.div),
              ("lift ifj,fe,fej->ei b=4", E.lift_fe), ("lift ef,fij,fej->ei b=4", E.lift_ef)]
     rows = []
@@ -61,8 +65,9 @@ def main() -> None:
         gops = sum(measure._get_giga_ops_from_einsum(e, n).values())
         gb = measure._get_footprint_gbytes(e, n)
         roof = measure.get_roofline_flop_rate(e, cq.device.name, n)[np.dtype(dt)]
-        print(f"| {name} | {dt} | {n} | {t * 1e3:.4f} | {gops / t:.0f} | {gb / t:.0f} | {roof:.0f} | {100 * gops / t / roof:.1f} |",
-              flush=True)
+        roof_sus = min(sus[dt], gops / gb * bw)       # the roofline with its FP leg at the sustained peak
+        print(f"| {name} | {dt} | {n} | {t * 1e3:.4f} | {gops / t:.0f} | {gb / t:.0f} | {roof:.0f} | {100 * gops / t / roof:.1f} | "
+              f"{100 * gops / t / roof_sus:.1f} |", flush=True)
 
 
 if __name__ == "__main__":
