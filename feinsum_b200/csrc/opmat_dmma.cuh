@@ -991,6 +991,14 @@ k_grad_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, 
 // ================================================================ LIFT =====
 // out_k[e,i] = sum_{f,j} Op(f,i,j) * Jf(e,f) * v_k[f,e,j];  K = (f,j) = 60 = 15 k-tiles
 // work item = (chunk, field): a slot holds one field of one chunk
+// position of the operator fragment of (k-tile, column tile, lane) in the table.  PAIRED: column tiles in pairs, so
+// that one LDS.128 feeds two of them (as the divergence kernel does): 30 instead of 60 fragment loads per item.  Taken
+// by the TMA = false instantiations only (E = 4 000 001: 73.5 -> 75.0 % of roofline); the same change makes the TMA
+// instantiation 3 % slower (2.305 -> 2.370 ms at E = 4 M, A/B on one box) -- ptxas' allocation again.
+template <bool PAIRED>
+__device__ __forceinline__ int lift_b_pos(int kt, int nt, int ln) {
+  return PAIRED ? ((kt * 2 + (nt >> 1)) * 32 + ln) * 2 + (nt & 1) : (kt * kNT + nt) * 32 + ln;
+}
 struct LiftLayout {
   static constexpr int KT = 15;
   static constexpr int B_MAIN = KT * kNT * 32;                        // 1920
@@ -1158,7 +1166,7 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
         const int ln = idx & 31, nt = (idx >> 5) % kNT, kt = (idx >> 5) / kNT;
         const int g = ln >> 2, t = ln & 3, k = 4 * kt + t, f = k / 15, j = k - 15 * f;
         const int i = 8 * nt + g;
-        sB[idx] = FE ? stages[(i * 4 + f) * 15 + j] : stages[(f * 35 + i) * 15 + j];
+        sB[TMA ? idx : lift_b_pos<true>(kt, nt, ln)] = FE ? stages[(i * 4 + f) * 15 + j] : stages[(f * 35 + i) * 15 + j];
       }
     }
     for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
@@ -1176,7 +1184,7 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
       const int ln = idx & 31, nt = (idx >> 5) % kNT, kt = (idx >> 5) / kNT;
       const int g = ln >> 2, t = ln & 3, k = 4 * kt + t, f = k / 15, j = k - 15 * f;
       const int i = 8 * nt + g;
-      sB[idx] = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
+      sB[TMA ? idx : lift_b_pos<true>(kt, nt, ln)] = FE ? Og[(i * 4 + f) * 15 + j] : Og[(f * 35 + i) * 15 + j];
     }
     _Pragma("unroll 4")   // independent operator loads in flight (matters at small E)
     for (int idx = threadIdx.x; idx < L::B_LEFT; idx += blockDim.x) {
@@ -1266,12 +1274,24 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
     {
 #pragma unroll
     for (int kt = 0; kt < L::KT; ++kt) {
-      const double* bp = sB + (kt * kNT) * 32 + lane;
+      if constexpr (!TMA) {                      // paired fragments, see lift_b_pos
+        const double2 b01 = *reinterpret_cast<const double2*>(sB + ((kt * 2 + 0) * 32 + lane) * 2);
+        const double2 b23 = *reinterpret_cast<const double2*>(sB + ((kt * 2 + 1) * 32 + lane) * 2);
 #pragma unroll
-      for (int nt = 0; nt < kNT; ++nt) {
-        const double b = bp[nt * 32];
+        for (int m = 0; m < kME; ++m) {
+          dmma884(acc[m][0], a[m][kt], b01.x);
+          dmma884(acc[m][1], a[m][kt], b01.y);
+          dmma884(acc[m][2], a[m][kt], b23.x);
+          dmma884(acc[m][3], a[m][kt], b23.y);
+        }
+      } else {
+        const double* bp = sB + (kt * kNT) * 32 + lane;
 #pragma unroll
-        for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m][kt], b);
+        for (int nt = 0; nt < kNT; ++nt) {
+          const double b = bp[nt * 32];
+#pragma unroll
+          for (int m = 0; m < kME; ++m) dmma884(acc[m][nt], a[m][kt], b);
+        }
       }
       const double2 l01 = *reinterpret_cast<const double2*>(sL + (kt * 4 + t) * 4);
       const double l2 = sL[(kt * 4 + t) * 4 + 2];
