@@ -130,15 +130,6 @@ __device__ __forceinline__ double2 lds_v2(uint32_t addr) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
   return v;
 }
-// c += a * b as a volatile asm statement (stays between the DMMAs it was written between)
-__device__ __forceinline__ void dfma_inplace(double& c, double a, double b) {
-  asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(c) : "d"(a), "d"(b));
-}
-__device__ __forceinline__ double lds_f64(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
 __device__ __forceinline__ double quad_sum(double v) {   // sum over the 4 lanes sharing g
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -227,13 +218,6 @@ __device__ __forceinline__ int odd8(const void* p) { return (int)((reinterpret_c
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
-
-// f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N - 1>{}): a loop whose index is a constant
-// expression inside the body (usable as an asm immediate)
-template <class F, int... I>
-__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) { (f(std::integral_constant<int, I>{}), ...); }
-template <int N, class F>
-__device__ __forceinline__ void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
 
 // lets a kernel launched with programmatic stream serialization behind this one start as SMs free up (launch_k)
 __device__ __forceinline__ void release_dependent_kernels() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
