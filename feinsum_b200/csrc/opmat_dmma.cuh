@@ -618,7 +618,12 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
     // cycles: with the 32 accumulator registers free again there is room for kLP partial sums per value
     // (6 kLP independent chains), which makes this tail issue bound (2 cycles per DFMA) instead of
     // latency bound (ptxas groups the DFMAs behind the DMMAs wherever they are written).
-    constexpr int kLP = 4;
+    // kLP swept on one box with the final kernel (bench.py div_p4, E = 4 M): 2: 1.072 ms, 3: 1.049, 4: 1.056,
+    // 5: 1.028, 6: 1.029, 7: 1.032, 8: 1.041, 9: 1.047; 6 is also the best for the NX = 1 instantiation (se_p4)
+#ifndef FNSM_KLP
+#define FNSM_KLP 6
+#endif
+    constexpr int kLP = FNSM_KLP;
     double accL[kLP][kME][kNL];
 #pragma unroll
     for (int p = 0; p < kLP; ++p)
@@ -652,7 +657,12 @@ k_div_dmma(const __grid_constant__ OpMaps maps, const double* __restrict__ Jg, c
       for (int m = 0; m < kME; ++m) {
         double l[kNL];
 #pragma unroll
-        for (int d = 0; d < kNL; ++d) l[d] = quad_sum((accL[0][m][d] + accL[1][m][d]) + (accL[2][m][d] + accL[3][m][d]));
+        for (int d = 0; d < kNL; ++d) {
+          double sacc = accL[0][m][d];
+#pragma unroll
+          for (int p = 1; p < kLP; ++p) sacc += accL[p][m][d];
+          l[d] = quad_sum(sacc);
+        }
         const double lv = t == 0 ? l[0] : (t == 1 ? l[1] : l[2]);
         if (STAGED) {
           if (t < kNL) stage[chunk_el(g, m) * 35 + 32 + t] = lv;
@@ -1247,13 +1257,19 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
     if (!FS && advance) tk = wq.ticket(lane);      // ticket after next; its latency hides under the DMMAs
 
     double acc[kME][kNT][2];
-    double accL[2][kME][kNL];      // two partial sums per value: DFMA latency >> 6 chains
+#ifndef FNSM_LIFT_LP
+#define FNSM_LIFT_LP 2
+#endif
+    constexpr int kLLP = FNSM_LIFT_LP;
+    double accL[kLLP][kME][kNL];   // partial sums per value: DFMA latency >> 6 chains
 #pragma unroll
     for (int m = 0; m < kME; ++m) {
 #pragma unroll
       for (int nt = 0; nt < kNT; ++nt) { acc[m][nt][0] = 0.0; acc[m][nt][1] = 0.0; }
 #pragma unroll
-      for (int d = 0; d < kNL; ++d) { accL[0][m][d] = 0.0; accL[1][m][d] = 0.0; }
+      for (int d = 0; d < kNL; ++d)
+#pragma unroll
+        for (int p = 0; p < kLLP; ++p) accL[p][m][d] = 0.0;
     }
     {
 #pragma unroll
@@ -1281,9 +1297,9 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
       const double l2 = sL[(kt * 4 + t) * 4 + 2];
 #pragma unroll
       for (int m = 0; m < kME; ++m) {
-        accL[kt & 1][m][0] = fma(a[m][kt], l01.x, accL[kt & 1][m][0]);
-        accL[kt & 1][m][1] = fma(a[m][kt], l01.y, accL[kt & 1][m][1]);
-        accL[kt & 1][m][2] = fma(a[m][kt], l2, accL[kt & 1][m][2]);
+        accL[kt % kLLP][m][0] = fma(a[m][kt], l01.x, accL[kt % kLLP][m][0]);
+        accL[kt % kLLP][m][1] = fma(a[m][kt], l01.y, accL[kt % kLLP][m][1]);
+        accL[kt % kLLP][m][2] = fma(a[m][kt], l2, accL[kt % kLLP][m][2]);
       }
     }
     }
@@ -1297,8 +1313,14 @@ k_lift_dmma(const __grid_constant__ LiftMaps maps, const double* __restrict__ Jg
 #pragma unroll
     for (int m = 0; m < kME; ++m) {
       double* o = stage + so + chunk_el(g, m) * 35;
-      const double l0 = quad_sum(accL[0][m][0] + accL[1][m][0]), l1 = quad_sum(accL[0][m][1] + accL[1][m][1]),
-                   l2 = quad_sum(accL[0][m][2] + accL[1][m][2]);
+      double ls[kNL];
+#pragma unroll
+      for (int d = 0; d < kNL; ++d) {
+        ls[d] = accL[0][m][d];
+#pragma unroll
+        for (int p = 1; p < kLLP; ++p) ls[d] += accL[p][m][d];
+      }
+      const double l0 = quad_sum(ls[0]), l1 = quad_sum(ls[1]), l2 = quad_sum(ls[2]);
 #pragma unroll
       for (int nt = 0; nt < kNT; ++nt) {
         o[8 * nt + 2 * t] = acc[m][nt][0];
