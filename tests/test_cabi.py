@@ -95,3 +95,21 @@ def test_se_shape_table_mirrors_the_library(lib):
                 for nj in (ni, ni + 1):
                     assert bool(lib.fnsm_b200_opmat_se_supported(code, ns, ni, nj)) == \
                         se_kernel_available(dt, ns, ni, nj), (dt, ns, ni, nj)
+
+
+def test_make_cfg_measurement_switches():
+    """``with_params`` keys that land in ``fnsm_cfg.reserved`` (include/fnsm_b200.h): flags -> [0], stagger -> [1],
+    dbgk -> bits 0-3 of [2], fast_start -> bits 4-5 of [2]; they do not disturb each other."""
+    from feinsum_b200 import _cabi
+    from feinsum_b200.diagnostics import InvalidParameterError
+
+    assert _cabi.make_cfg(None) is None and _cabi.make_cfg({}) is None
+    cfg = _cabi.make_cfg({"threads": 384, "variant": 1, "flags": 1, "stagger": 3000, "dbgk": 5, "fast_start": 2}).contents
+    assert (cfg.threads, cfg.variant) == (384, 1)
+    assert list(cfg.reserved) == [1, 3000, 5 | (2 << 4)]
+    cfg = _cabi.make_cfg({"fast_start": 1, "dbgk": 0}).contents
+    assert list(cfg.reserved) == [0, 0, 1 << 4]
+    cfg = _cabi.make_cfg({"dbgk": 7, "fast_start": 0}).contents
+    assert list(cfg.reserved) == [0, 0, 7]
+    with pytest.raises(InvalidParameterError):
+        _cabi.make_cfg({"no_such_knob": 1})
