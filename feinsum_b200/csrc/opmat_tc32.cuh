@@ -192,7 +192,9 @@ struct GradTC {
   static constexpr int NB = NP + N;                     // rows of the operator table: [hi | pad | lo] = 240
   // groups per CTA: the tiles of the lower orders are small (6-40 KB), so their fixed latencies (TMA, MMA
   // completion, group barriers) are covered by four independent groups instead of two
-  static constexpr int GROUPS = ND <= 10 ? 8 : (ND <= 20 ? 4 : 2);
+  // p = 2 (ND = 10): 4 / 6 / 7 / 8 groups = 79 / 90.5 / 88.8 / 86 % of roofline (8 groups = 1024 threads cap the
+  // kernel at 64 registers: 40 bytes of spills)
+  static constexpr int GROUPS = ND <= 4 ? 8 : (ND <= 10 ? 6 : (ND <= 20 ? 4 : 2));
   static constexpr int WPG = GROUPS == 2 ? 8 : 4, GT = 32 * WPG, NH = WPG / 4;   // warps / threads per group, threads per row
   static constexpr int THREADS = GROUPS * GT;
   static constexpr int B_LBO = NB * 16;                 // operator table: addr(n, k) = (k/4) B_LBO + 16 n + 4 (k%4)
@@ -204,7 +206,7 @@ struct GradTC {
   static constexpr int STAGE_BYTES = tc_pad(tc_max(OUT_BYTES, 2 * A_BYTES), 128);   // the A operand aliases the stage
   static constexpr int NQ = (ND + 7) / 8;               // epilogue passes of 8 dofs (24 columns)
   static constexpr int GROUP_BYTES = 2 * SLOT_BYTES + STAGE_BYTES;
-  static constexpr int TMEM_COLS_PER_GROUP = 512 / GROUPS;      // 256 (240 used)
+  static constexpr int TMEM_COLS_PER_GROUP = (512 / GROUPS) / 16 * 16;      // 256 (240 used)
   static constexpr size_t SMEM = B_BYTES + (size_t)GROUPS * GROUP_BYTES + 512;   // + mbarriers, TMEM base
   // non-TMA variant: every slab of the slots and of the stage carries kPlainPad bytes of slack for its shift
   static constexpr int OUT_SLAB_P = TM * ND * 4 + kPlainPad;
